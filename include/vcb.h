@@ -1,0 +1,148 @@
+/*
+ * vcb.h -- C ABI of libvcb.so: the B200 (sm_100a) fused ELBO + gradient path of VeloCycle.
+ *
+ * What this boundary replaces in the reference (lamanno-epfl/velocycle, working-tree line numbers):
+ *
+ *   vcb_phase_fwd_bwd     <->  velocycle/phase_inference_model.py:368-393
+ *                              (pack_direction -> torch_fourier_basis -> ElogS einsums ->
+ *                               pyro.sample("S", GammaPoisson(...), obs=mp.S)) plus the autograd
+ *                              backward of that block driven by pyro.infer.Trace_ELBO at :162/:169.
+ *   vcb_velocity_fwd_bwd  <->  velocycle/velocity_inference_model.py:344-386 (and the identical
+ *                              LRMN block :443-469): zeta, zeta', zeta_omega, ElogS, omega, ElogU and
+ *                              the two GammaPoisson sites "S" and "U", plus their backward (:111/:120).
+ *   vcb_count_histogram   <->  no reference counterpart; one-off data statistic that lets the
+ *                              parameter-only lgamma/digamma terms of GammaPoisson.log_prob
+ *                              (pyro/distributions/conjugate.py) leave the per-element loop.
+ *   vcb_clipped_adam      <->  pyro.optim.ClippedAdam.step (pyro/optim/clipped_adam.py), configured in
+ *                              tutorials/Tutorial_Capolupo_HumanFibroblasts_OneSample.ipynb cell 27.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller (torch tensors' data_ptr()); the library
+ *     never allocates or frees device memory and keeps no global state.  Scratch space is the
+ *     caller-provided workspace (size from vcb_workspace_bytes).
+ *   - All work is enqueued on the cudaStream_t passed as `void* stream`; nothing synchronises the
+ *     device, so every entry point is CUDA-graph capturable.
+ *   - Return value: 0 = OK; negative = argument error detected on the host (nothing launched);
+ *     positive = cudaError_t of a failed launch.  vcb_strerror() names both.
+ *   - Counts S/U: float32, cell-major ("[Nc][ld]", genes contiguous) -- the physical layout of the
+ *     reference's mp.S = S.T.float() (preprocessing.py:193-194, 308-309).  ld is the row pitch in
+ *     floats: a multiple of 4 with 16-byte aligned base pointers; columns Ng..ld-1 must be zero.
+ *   - Outputs are overwritten, never accumulated.
+ */
+#ifndef VCB_H
+#define VCB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCB_VERSION 100 /* 0.1.0 */
+
+#define VCB_MAX_HARMONICS 5 /* gene / angular-speed harmonics compiled in: H in 0..5 */
+
+/* flags */
+#define VCB_FLAG_GRAD 1u          /* also emit every gradient (otherwise log-prob sums only) */
+#define VCB_FLAG_LGAMMA_INLINE 2u /* evaluate lgamma/digamma terms per element instead of via the histogram */
+
+/* error codes (negative) */
+#define VCB_OK 0
+#define VCB_ERR_NULL -1        /* a required pointer is NULL */
+#define VCB_ERR_SIZE -2        /* a size is out of range */
+#define VCB_ERR_ALIGN -3       /* ld not a multiple of 4 or S/U/workspace not 16-byte aligned */
+#define VCB_ERR_HARMONICS -4   /* H or Hw above VCB_MAX_HARMONICS */
+#define VCB_ERR_WORKSPACE -5   /* workspace too small */
+#define VCB_ERR_SPECTRUM -6    /* histogram required (no VCB_FLAG_LGAMMA_INLINE) but not provided */
+#define VCB_ERR_DEVICE -7      /* not an sm_100 device / no device */
+
+/* Sparse per-gene histogram of one count matrix ("count spectrum"), built once per dataset:
+ * for gene g the distinct values k > 0 that occur are val[off[g] .. off[g+1]) with multiplicities mult[].
+ * lgk1[g] = sum_c lgamma(k_gc + 1) (parameter-free part of the log-pmf). */
+typedef struct vcb_spectrum {
+  const int32_t* off;  /* [Ng+1] */
+  const float* val;    /* [nnz]  */
+  const float* mult;   /* [nnz]  */
+  const double* lgk1;  /* [Ng]   */
+} vcb_spectrum_t;
+
+typedef struct vcb_problem {
+  int64_t Nc; /* cells held by this rank */
+  int64_t Ng; /* genes */
+  int64_t ld; /* row pitch of S and U in floats */
+  int32_t H;  /* gene harmonics, K = 2H+1                      (mp.num_harmonics_S / kwargs zeta)      */
+  int32_t Hw; /* angular-speed harmonics, Kw = 2Hw+1             (kwargs zeta_omega; velocity only)     */
+  int32_t Nb; /* rows of dnu; 0 = no batch offset term          (mp.Nb, mp.with_delta_nu)              */
+  int32_t Nx; /* rows of nu_omega                               (mp.Nx; velocity only)                 */
+  uint32_t flags;
+  uint32_t reserved;
+
+  /* observed counts */
+  const float* S; /* [Nc][ld] */
+  const float* U; /* [Nc][ld], velocity only */
+
+  /* per-cell inputs */
+  const float* phi;        /* [Nc] phase angle (atan2 of the phixy sample stays in torch) */
+  const float* cf;         /* [Nc] mp.count_factor                                          */
+  const int32_t* batch_id; /* [Nc] argmax of the one-hot mp.Db column, NULL = all 0         */
+  const int32_t* cond_id;  /* [Nc] argmax of the one-hot mp.D column,  NULL = all 0         */
+
+  /* per-gene inputs */
+  const float* nu;        /* [Ng][K]  Fourier coefficients, order [1, sin, cos, sin2, cos2, ...] */
+  const float* dnu;       /* [Nb][Ng] batch offsets (Delta-nu), NULL when Nb == 0               */
+  const float* shape_inv; /* [Ng]     NB dispersion, r = 1/shape_inv                            */
+  const float* logbeta;   /* [Ng]     velocity only                                             */
+  const float* gamma;     /* [Ng]     exp(log gamma), velocity only                             */
+  const float* nu_omega;  /* [Nx][Kw] velocity only                                             */
+
+  /* count spectra (ignored under VCB_FLAG_LGAMMA_INLINE) */
+  vcb_spectrum_t spec_S;
+  vcb_spectrum_t spec_U;
+
+  /* outputs: per-gene log-prob sums over this rank's cells */
+  float* lp_S; /* [Ng] */
+  float* lp_U; /* [Ng] velocity only */
+
+  /* outputs: gradients of sum(lp_S)+sum(lp_U); only written under VCB_FLAG_GRAD; any may be NULL */
+  float* d_nu;        /* [Ng][K]  */
+  float* d_dnu;       /* [Nb][Ng] */
+  float* d_shape_inv; /* [Ng]     */
+  float* d_logbeta;   /* [Ng]     */
+  float* d_gamma;     /* [Ng]     */
+  float* d_nu_omega;  /* [Nx][Kw] */
+  float* d_phi;       /* [Nc] total derivative (includes the path through omega(phi)) */
+  float* d_cf;        /* [Nc]     */
+  float* d_omega;     /* [Nc] partial w.r.t. the per-cell angular speed (informational) */
+} vcb_problem_t;
+
+int vcb_version(void);
+const char* vcb_strerror(int code);
+
+/* Bytes of device scratch the two fwd_bwd entry points need for this problem (16-byte aligned base). */
+size_t vcb_workspace_bytes(const vcb_problem_t* p);
+
+/* Phase (manifold-learning) model: spliced counts only. */
+int vcb_phase_fwd_bwd(const vcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Velocity model: spliced + unspliced counts in the same pass. */
+int vcb_velocity_fwd_bwd(const vcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Dense per-gene histogram of one count matrix: hist[g*B + min(k, B-1)] += 1 (uint32, caller zeroes it).
+ * status[0] is set non-zero if a value is negative, non-integer or >= B-1 (caller zeroes it too). */
+int vcb_count_histogram(const float* M, int64_t Nc, int64_t Ng, int64_t ld, int32_t B, uint32_t* hist,
+                        int32_t* status, void* stream);
+
+/* Multi-tensor ClippedAdam over one flat fp32 buffer of n elements:
+ *   lr_t = lr0 * lrd^step (step counts from 1, read from device memory so that graphs replay),
+ *   g = clamp(g, -clip, clip); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *   p -= lr_t * sqrt(1-b2^step)/(1-b1^step) * m / (sqrt(v) + eps).
+ * `step_dev` points at an int64 step counter that this call increments first. */
+int vcb_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     int64_t* step_dev, float lr0, float lrd, float beta1, float beta2, float eps,
+                     float clip, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCB_H */

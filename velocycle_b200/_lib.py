@@ -1,0 +1,97 @@
+"""ctypes binding of ``libvcb.so`` (C ABI declared in ``include/vcb.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (plain ``nvcc -shared``); there is no
+fallback: if it is missing, importing anything that needs it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvcb.so")
+
+VCB_FLAG_GRAD = 1
+VCB_FLAG_LGAMMA_INLINE = 2
+VCB_MAX_HARMONICS = 5
+
+c_float_p = C.c_void_p  # device pointers travel as integers
+
+
+class VcbSpectrum(C.Structure):
+    _fields_ = [("off", C.c_void_p), ("val", C.c_void_p), ("mult", C.c_void_p), ("lgk1", C.c_void_p)]
+
+
+class VcbProblem(C.Structure):
+    _fields_ = [
+        ("Nc", C.c_int64), ("Ng", C.c_int64), ("ld", C.c_int64),
+        ("H", C.c_int32), ("Hw", C.c_int32), ("Nb", C.c_int32), ("Nx", C.c_int32),
+        ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("S", C.c_void_p), ("U", C.c_void_p),
+        ("phi", C.c_void_p), ("cf", C.c_void_p), ("batch_id", C.c_void_p), ("cond_id", C.c_void_p),
+        ("nu", C.c_void_p), ("dnu", C.c_void_p), ("shape_inv", C.c_void_p),
+        ("logbeta", C.c_void_p), ("gamma", C.c_void_p), ("nu_omega", C.c_void_p),
+        ("spec_S", VcbSpectrum), ("spec_U", VcbSpectrum),
+        ("lp_S", C.c_void_p), ("lp_U", C.c_void_p),
+        ("d_nu", C.c_void_p), ("d_dnu", C.c_void_p), ("d_shape_inv", C.c_void_p),
+        ("d_logbeta", C.c_void_p), ("d_gamma", C.c_void_p), ("d_nu_omega", C.c_void_p),
+        ("d_phi", C.c_void_p), ("d_cf", C.c_void_p), ("d_omega", C.c_void_p),
+    ]
+
+
+EXPORTS = (
+    "vcb_version",
+    "vcb_strerror",
+    "vcb_workspace_bytes",
+    "vcb_phase_fwd_bwd",
+    "vcb_velocity_fwd_bwd",
+    "vcb_count_histogram",
+    "vcb_clipped_adam",
+)
+
+_lib: Optional[C.CDLL] = None
+
+
+class VcbError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libvcb.so once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VcbError(
+            f"{LIB_PATH} not found: the CUDA library has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root (needs nvcc). "
+            "velocycle_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.vcb_version.restype = C.c_int
+    lib.vcb_strerror.restype = C.c_char_p
+    lib.vcb_strerror.argtypes = [C.c_int]
+    lib.vcb_workspace_bytes.restype = C.c_size_t
+    lib.vcb_workspace_bytes.argtypes = [C.POINTER(VcbProblem)]
+    for name in ("vcb_phase_fwd_bwd", "vcb_velocity_fwd_bwd"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(VcbProblem), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.vcb_count_histogram.restype = C.c_int
+    lib.vcb_count_histogram.argtypes = [
+        C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+    ]
+    lib.vcb_clipped_adam.restype = C.c_int
+    lib.vcb_clipped_adam.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+        C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
+    ]
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str = "libvcb") -> None:
+    if code != 0:
+        msg = load().vcb_strerror(code).decode()
+        raise VcbError(f"{what} failed with code {code}: {msg}")

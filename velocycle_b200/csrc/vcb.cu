@@ -1,0 +1,591 @@
+// libvcb: C-ABI entry points (include/vcb.h), the small per-cell / per-gene kernels around the
+// streaming kernel (vcb_stream.cuh), the count histogram and the fused ClippedAdam.
+#include "vcb.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "vcb_common.cuh"
+#include "vcb_stream.cuh"
+
+namespace vcb {
+
+// ======================================================================================================
+// Per-cell prologue: Fourier tables.  One thread per cell.
+//   row = [zeta_1..zeta_2H | zeta'_1..zeta'_2H | zeta''_1..zeta''_2H | omega | cf | batch | pad]
+// Column order [sin, cos] per harmonic and sin(fl(n*phi)) follow utils.py:420-435.
+// ======================================================================================================
+struct CellParams {
+  const float* phi;
+  const float* cf;
+  const int32_t* batch_id;
+  const int32_t* cond_id;
+  const float* nu_omega;  // [Nx][Kw] or null
+  float* tab;
+  long long Nc;
+  int H, Hw, Nx, tabw;
+};
+
+__global__ void vcb_cell_tables_kernel(const CellParams P) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.Nc) return;
+  const float phi = P.phi[c];
+  float* row = P.tab + c * P.tabw;
+  const int H = P.H;
+  for (int n = 1; n <= H; ++n) {
+    float s, co;
+    const float fn = (float)n;
+    sincosf(fn * phi, &s, &co);
+    row[2 * n - 2] = s;
+    row[2 * n - 1] = co;
+    row[2 * H + 2 * n - 2] = fn * co;
+    row[2 * H + 2 * n - 1] = -fn * s;
+    row[4 * H + 2 * n - 2] = -fn * fn * s;
+    row[4 * H + 2 * n - 1] = -fn * fn * co;
+  }
+  float omega = 0.f;
+  if (P.nu_omega != nullptr) {
+    const int x = P.cond_id ? P.cond_id[c] : 0;
+    const int Kw = 2 * P.Hw + 1;
+    const float* nw = P.nu_omega + (long long)x * Kw;
+    omega = nw[0];
+    for (int n = 1; n <= P.Hw; ++n) {
+      float s, co;
+      sincosf((float)n * phi, &s, &co);
+      omega = fmaf(nw[2 * n - 1], s, omega);
+      omega = fmaf(nw[2 * n], co, omega);
+    }
+  }
+  row[6 * H] = omega;
+  row[6 * H + 1] = P.cf ? P.cf[c] : 0.f;
+  row[6 * H + 2] = __int_as_float(P.batch_id ? P.batch_id[c] : 0);
+  for (int i = 6 * H + 3; i < P.tabw; ++i) row[i] = 0.f;
+}
+
+// ======================================================================================================
+// Per-cell epilogue: sum the gene-tile partials, add the omega(phi) path to d/dphi, reduce d/dnu_omega.
+// ======================================================================================================
+struct CellEpiParams {
+  const float* cellpart;  // [n_tiles][NQ][Nc]
+  const float* phi;
+  const int32_t* cond_id;
+  const float* nu_omega;
+  float* d_phi;
+  float* d_cf;
+  float* d_omega;
+  double* dnw_acc;  // [Nx*Kw], zeroed
+  long long Nc;
+  int n_tiles, NQ, Hw, Nx;
+};
+
+__global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
+  extern __shared__ double s_acc[];  // [Nx*Kw]
+  const bool velo = P.NQ == 3;
+  const int Kw = 2 * P.Hw + 1;
+  const int nacc = velo ? P.Nx * Kw : 0;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) s_acc[i] = 0.0;
+  __syncthreads();
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < P.Nc) {
+    float q[3] = {0.f, 0.f, 0.f};
+    for (int t = 0; t < P.n_tiles; ++t)
+      for (int i = 0; i < P.NQ; ++i) q[i] += P.cellpart[((long long)t * P.NQ + i) * P.Nc + c];
+    float dphi = q[1];
+    if (velo) {
+      const float phi = P.phi[c];
+      const int x = P.cond_id ? P.cond_id[c] : 0;
+      const float* nw = P.nu_omega + (long long)x * Kw;
+      const float pom = q[2];
+      float domega_dphi = 0.f;
+      atomicAdd(&s_acc[x * Kw], (double)pom);
+      for (int n = 1; n <= P.Hw; ++n) {
+        float s, co;
+        const float fn = (float)n;
+        sincosf(fn * phi, &s, &co);
+        domega_dphi = fmaf(nw[2 * n - 1], fn * co, domega_dphi);
+        domega_dphi = fmaf(nw[2 * n], -fn * s, domega_dphi);
+        atomicAdd(&s_acc[x * Kw + 2 * n - 1], (double)(pom * s));
+        atomicAdd(&s_acc[x * Kw + 2 * n], (double)(pom * co));
+      }
+      dphi = fmaf(pom, domega_dphi, dphi);
+      if (P.d_omega) P.d_omega[c] = pom;
+    }
+    if (P.d_cf) P.d_cf[c] = q[0];
+    if (P.d_phi) P.d_phi[c] = dphi;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x)
+    if (s_acc[i] != 0.0) atomicAdd(&P.dnw_acc[i], s_acc[i]);
+}
+
+// ======================================================================================================
+// Per-gene epilogue: sum the cell-split partials in fp64, add the parameter-only terms
+// (n r log r, the lgamma / digamma sums over the count spectrum), apply the chain-rule factors.
+// Block = 32 genes x 8 lanes.
+// ======================================================================================================
+struct GeneEpiParams {
+  const float* genepart;  // [n_split][ROWS][ld]
+  const float* shape_inv;
+  const float* dnu_acc;  // [Nb][Ng] or null
+  const double* dnw_acc;
+  vcb_spectrum_t spec_S, spec_U;
+  float *lp_S, *lp_U, *d_nu, *d_dnu, *d_shape_inv, *d_logbeta, *d_gamma, *d_nu_omega;
+  long long Nc, Ng, ld;
+  int n_split, H, Nb, Nx, Hw;
+  int velo, grad, lginline;
+};
+
+constexpr int kEpiGenes = 32;
+constexpr int kEpiLanes = 8;
+constexpr int kEpiMaxRows = ROW_DNU + 2 * VCB_MAX_HARMONICS + 1;
+
+__device__ __forceinline__ void spectrum_sums(const vcb_spectrum_t& sp, long long g, double r, int lane, int nlanes,
+                                              double& lg_sum, double& psi_sum) {
+  lg_sum = 0.0;
+  psi_sum = 0.0;
+  if (sp.off == nullptr) return;
+  const int e0 = sp.off[g], e1 = sp.off[g + 1];
+  if (e1 <= e0) return;
+  const double lgr = lgamma(r), psr = digamma_d(r);
+  for (int e = e0 + lane; e < e1; e += nlanes) {
+    const double k = (double)sp.val[e], m = (double)sp.mult[e];
+    lg_sum += m * (lgamma(r + k) - lgr);
+    psi_sum += m * (digamma_d(r + k) - psr);
+  }
+}
+
+__global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel(const GeneEpiParams P) {
+  __shared__ double s_rows[kEpiMaxRows][kEpiGenes];
+  __shared__ double s_spec[4][kEpiLanes][kEpiGenes];
+  const int gx = threadIdx.x % kEpiGenes, ly = threadIdx.x / kEpiGenes;
+  const long long g = (long long)blockIdx.x * kEpiGenes + gx;
+  const int K = 2 * P.H + 1;
+  const int ROWS = ROW_DNU + K;
+  const bool valid = g < P.Ng;
+
+  for (int row = ly; row < ROWS; row += kEpiLanes) {
+    double s = 0.0;
+    const bool used = (row == ROW_AS || row == ROW_LS) || (P.velo && (row == ROW_AU || row == ROW_LU)) ||
+                      (P.velo && P.grad && (row == ROW_GU || row == ROW_W)) || (P.lginline && row == ROW_PSI) ||
+                      (P.grad && row >= ROW_DNU);
+    if (valid && used) {
+      const float* src = P.genepart + (long long)row * P.ld + g;
+      const long long stride = (long long)ROWS * P.ld;
+      for (int sidx = 0; sidx < P.n_split; ++sidx) s += (double)src[sidx * stride];
+    }
+    s_rows[row][gx] = s;
+  }
+  double r = 1.0;
+  if (valid) r = 1.0 / (double)P.shape_inv[g];
+  {
+    double a = 0, b = 0, c = 0, d = 0;
+    if (valid && !P.lginline) {
+      spectrum_sums(P.spec_S, g, r, ly, kEpiLanes, a, b);
+      if (P.velo) spectrum_sums(P.spec_U, g, r, ly, kEpiLanes, c, d);
+    }
+    s_spec[0][ly][gx] = a;
+    s_spec[1][ly][gx] = b;
+    s_spec[2][ly][gx] = c;
+    s_spec[3][ly][gx] = d;
+  }
+  __syncthreads();
+
+  if (ly == 0 && valid) {
+    double lgS = 0, psS = 0, lgU = 0, psU = 0;
+    for (int l = 0; l < kEpiLanes; ++l) {
+      lgS += s_spec[0][l][gx];
+      psS += s_spec[1][l][gx];
+      lgU += s_spec[2][l][gx];
+      psU += s_spec[3][l][gx];
+    }
+    if (!P.lginline) {
+      if (P.spec_S.lgk1) lgS -= P.spec_S.lgk1[g];
+      if (P.velo && P.spec_U.lgk1) lgU -= P.spec_U.lgk1[g];
+    }
+    const double n = (double)P.Nc;
+    const double lnr = log(r);
+    const double AS = s_rows[ROW_AS][gx] * kLn2d, LS = s_rows[ROW_LS][gx] * kLn2d;
+    const double lpS = AS - r * LS + n * r * lnr + lgS;
+    P.lp_S[g] = (float)lpS;
+    double LU = 0.0;
+    if (P.velo) {
+      const double AU = s_rows[ROW_AU][gx] * kLn2d;
+      LU = s_rows[ROW_LU][gx] * kLn2d;
+      P.lp_U[g] = (float)(AU - r * LU + n * r * lnr + lgU);
+    }
+    if (P.grad) {
+      double dnu0 = s_rows[ROW_DNU][gx];
+      if (P.Nb > 0 && P.dnu_acc != nullptr) {
+        dnu0 = 0.0;
+        for (int b = 0; b < P.Nb; ++b) {
+          const float v = P.dnu_acc[(long long)b * P.Ng + g];
+          dnu0 += (double)v;
+          if (P.d_dnu) P.d_dnu[(long long)b * P.Ng + g] = v;
+        }
+      }
+      if (P.d_nu) {
+        P.d_nu[g * K] = (float)dnu0;
+        for (int k = 1; k < K; ++k) P.d_nu[g * K + k] = (float)s_rows[ROW_DNU + k][gx];
+      }
+      const double psi = P.lginline ? s_rows[ROW_PSI][gx] : (psS + psU);
+      const double nmat = P.velo ? 2.0 : 1.0;
+      const double dr = psi + nmat * n * lnr - (LS + LU) - dnu0 / r;
+      if (P.d_shape_inv) P.d_shape_inv[g] = (float)(-r * r * dr);
+      if (P.velo) {
+        if (P.d_logbeta) P.d_logbeta[g] = (float)(-s_rows[ROW_GU][gx]);
+        if (P.d_gamma) P.d_gamma[g] = (float)s_rows[ROW_W][gx];
+      }
+    }
+  }
+  if (blockIdx.x == 0 && P.velo && P.grad && P.d_nu_omega != nullptr) {
+    const int n = P.Nx * (2 * P.Hw + 1);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) P.d_nu_omega[i] = (float)P.dnw_acc[i];
+  }
+}
+
+// ======================================================================================================
+// One-off dataset statistic: dense per-gene histogram of a count matrix.
+// A thread walks one gene column of a cell chunk; zeros are counted in a register.
+// ======================================================================================================
+__global__ void vcb_count_histogram_kernel(const float* __restrict__ M, long long Nc, long long Ng, long long ld, int B,
+                                           unsigned int* hist, int* status, int cells_per_block) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Ng) return;
+  const long long c0 = (long long)blockIdx.y * cells_per_block;
+  long long c1 = c0 + cells_per_block;
+  if (c1 > Nc) c1 = Nc;
+  unsigned int zeros = 0;
+  bool bad = false;
+  for (long long c = c0; c < c1; ++c) {
+    const float v = M[c * ld + g];
+    if (v == 0.f) {
+      ++zeros;
+    } else {
+      if (!(v > 0.f) || v != floorf(v) || v >= (float)(B - 1)) {
+        bad = true;
+        if (!(v > 0.f)) continue;
+      }
+      const int k = v >= (float)(B - 1) ? B - 1 : (int)v;
+      atomicAdd(&hist[g * B + k], 1u);
+    }
+  }
+  if (zeros) atomicAdd(&hist[g * B], zeros);
+  if (bad) atomicExch(status, 1);
+}
+
+// ======================================================================================================
+// Fused multi-tensor ClippedAdam (pyro/optim/clipped_adam.py semantics, lr decayed before use).
+// ======================================================================================================
+__global__ void vcb_adam_tick_kernel(long long* step) { *step += 1; }
+
+__global__ void vcb_clipped_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                        float* __restrict__ v, long long n, const long long* step_dev, float lr0,
+                                        float lrd, float b1, float b2, float eps, float clip) {
+  const double step = (double)(*step_dev);
+  const double lr = (double)lr0 * pow((double)lrd, step);
+  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  const float step_size = (float)(lr * sqrt(bc2) / bc1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    gi = fminf(fmaxf(gi, -clip), clip);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - step_size * (mi / (sqrtf(vi) + eps));
+  }
+}
+
+// ======================================================================================================
+// Host side
+// ======================================================================================================
+struct Plan {
+  int nthr, tile_g, n_tiles, n_split, W_max;
+  int tabw, rows, NQ;
+  size_t off_tab, off_genepart, off_cellpart, off_dnuacc, off_dnwacc, total;
+  int smem;
+};
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else
+      n = 148;
+  }
+  return n;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Plan make_plan(const vcb_problem_t* p, bool velo) {
+  Plan pl{};
+  const bool grad = (p->flags & VCB_FLAG_GRAD) != 0;
+  // threads per CTA: the widest tile that wastes the fewest lanes
+  const int cand[5] = {512, 256, 128, 64, 32};
+  double best = -1.0;
+  for (int i = 0; i < 5; ++i) {
+    const long long tg = 4LL * cand[i];
+    const long long nt = (p->ld + tg - 1) / tg;
+    const double eff = (double)p->ld / (double)(nt * tg);
+    if (eff > best + 0.02) {
+      best = eff;
+      pl.nthr = cand[i];
+    }
+  }
+  pl.tile_g = 4 * pl.nthr;
+  pl.n_tiles = (int)((p->ld + pl.tile_g - 1) / pl.tile_g);
+  if (pl.n_tiles < 1) pl.n_tiles = 1;
+  pl.W_max = (int)(p->ld < pl.tile_g ? p->ld : pl.tile_g);
+  const int ctas_per_sm = kMaxThreads / pl.nthr;
+  long long ns = ((long long)sm_count() * ctas_per_sm) / pl.n_tiles;
+  const long long max_split = (p->Nc + kCellsPerStage - 1) / kCellsPerStage;
+  if (ns > max_split) ns = max_split;
+  if (ns < 1) ns = 1;
+  pl.n_split = (int)ns;
+  pl.tabw = table_width(p->H);
+  pl.rows = gene_rows(p->H);
+  pl.NQ = velo ? 3 : 2;
+  pl.smem = stream_smem_layout(p->H, velo, grad, pl.nthr, pl.W_max).total;
+  size_t off = 0;
+  pl.off_tab = off;
+  off = align_up(off + (size_t)p->Nc * pl.tabw * 4, 256);
+  pl.off_genepart = off;
+  off = align_up(off + (size_t)pl.n_split * pl.rows * p->ld * 4, 256);
+  pl.off_cellpart = off;
+  off = align_up(off + (size_t)pl.n_tiles * pl.NQ * p->Nc * 4, 256);
+  pl.off_dnuacc = off;
+  off = align_up(off + (size_t)(p->Nb > 0 ? p->Nb : 0) * p->Ng * 4, 256);
+  pl.off_dnwacc = off;
+  off = align_up(off + (size_t)(p->Nx > 0 ? p->Nx : 1) * (2 * p->Hw + 1) * 8, 256);
+  pl.total = off;
+  return pl;
+}
+
+static int validate(const vcb_problem_t* p, bool velo) {
+  if (p == nullptr) return VCB_ERR_NULL;
+  if (p->Nc < 0 || p->Ng <= 0 || p->ld < p->Ng || p->Nc > (1LL << 40) || p->Ng > (1LL << 24)) return VCB_ERR_SIZE;
+  if (p->H < 0 || p->H > VCB_MAX_HARMONICS) return VCB_ERR_HARMONICS;
+  if (p->Nb < 0) return VCB_ERR_SIZE;
+  if (p->ld % 4 != 0) return VCB_ERR_ALIGN;
+  if (!p->S || !p->phi || !p->nu || !p->shape_inv || !p->lp_S) return VCB_ERR_NULL;
+  if (((uintptr_t)p->S & 15) != 0) return VCB_ERR_ALIGN;
+  if (p->Nb > 0 && (!p->dnu || !p->batch_id)) return VCB_ERR_NULL;
+  if (velo) {
+    if (p->Hw < 0 || p->Hw > VCB_MAX_HARMONICS) return VCB_ERR_HARMONICS;
+    if (p->Nx < 1) return VCB_ERR_SIZE;
+    if (!p->U || !p->logbeta || !p->gamma || !p->nu_omega || !p->lp_U) return VCB_ERR_NULL;
+    if (((uintptr_t)p->U & 15) != 0) return VCB_ERR_ALIGN;
+    if (p->Nx > 1 && !p->cond_id) return VCB_ERR_NULL;
+  }
+  if (!(p->flags & VCB_FLAG_LGAMMA_INLINE)) {
+    if (!p->spec_S.off || !p->spec_S.val || !p->spec_S.mult || !p->spec_S.lgk1) return VCB_ERR_SPECTRUM;
+    if (velo && (!p->spec_U.off || !p->spec_U.val || !p->spec_U.mult || !p->spec_U.lgk1)) return VCB_ERR_SPECTRUM;
+  }
+  return VCB_OK;
+}
+
+template <int H, bool VELO, bool GRAD, bool LGI>
+static cudaError_t launch_stream_t(const StreamParams& sp, dim3 grid, int nthr, int smem, cudaStream_t st) {
+  auto kfn = vcb_stream_kernel<H, VELO, GRAD, LGI>;
+  static int configured_smem = 0;  // per instantiation; raising the opt-in limit is idempotent
+  if (smem > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured_smem = smem;
+  }
+  kfn<<<grid, nthr, smem, st>>>(sp);
+  return cudaGetLastError();
+}
+
+template <int H>
+static cudaError_t launch_stream_h(bool velo, bool grad, bool lgi, const StreamParams& sp, dim3 grid, int nthr,
+                                   int smem, cudaStream_t st) {
+  if (velo) {
+    if (grad) return lgi ? launch_stream_t<H, true, true, true>(sp, grid, nthr, smem, st)
+                         : launch_stream_t<H, true, true, false>(sp, grid, nthr, smem, st);
+    return lgi ? launch_stream_t<H, true, false, true>(sp, grid, nthr, smem, st)
+               : launch_stream_t<H, true, false, false>(sp, grid, nthr, smem, st);
+  }
+  if (grad) return lgi ? launch_stream_t<H, false, true, true>(sp, grid, nthr, smem, st)
+                       : launch_stream_t<H, false, true, false>(sp, grid, nthr, smem, st);
+  return lgi ? launch_stream_t<H, false, false, true>(sp, grid, nthr, smem, st)
+             : launch_stream_t<H, false, false, false>(sp, grid, nthr, smem, st);
+}
+
+static cudaError_t launch_stream(int H, bool velo, bool grad, bool lgi, const StreamParams& sp, dim3 grid, int nthr,
+                                 int smem, cudaStream_t st) {
+  switch (H) {
+    case 0: return launch_stream_h<0>(velo, grad, lgi, sp, grid, nthr, smem, st);
+    case 1: return launch_stream_h<1>(velo, grad, lgi, sp, grid, nthr, smem, st);
+    case 2: return launch_stream_h<2>(velo, grad, lgi, sp, grid, nthr, smem, st);
+    case 3: return launch_stream_h<3>(velo, grad, lgi, sp, grid, nthr, smem, st);
+    case 4: return launch_stream_h<4>(velo, grad, lgi, sp, grid, nthr, smem, st);
+    case 5: return launch_stream_h<5>(velo, grad, lgi, sp, grid, nthr, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_bytes, void* stream) {
+  int rc = validate(p, velo);
+  if (rc != VCB_OK) return rc;
+  const Plan pl = make_plan(p, velo);
+  if (workspace == nullptr) return VCB_ERR_NULL;
+  if (((uintptr_t)workspace & 15) != 0) return VCB_ERR_ALIGN;
+  if (ws_bytes < pl.total) return VCB_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool grad = (p->flags & VCB_FLAG_GRAD) != 0;
+  const bool lgi = (p->flags & VCB_FLAG_LGAMMA_INLINE) != 0;
+  unsigned char* ws = (unsigned char*)workspace;
+  float* tab = (float*)(ws + pl.off_tab);
+  float* genepart = (float*)(ws + pl.off_genepart);
+  float* cellpart = (float*)(ws + pl.off_cellpart);
+  float* dnu_acc = p->Nb > 0 ? (float*)(ws + pl.off_dnuacc) : nullptr;
+  double* dnw_acc = (double*)(ws + pl.off_dnwacc);
+  cudaError_t e;
+
+  if (grad) {
+    if (dnu_acc) {
+      e = cudaMemsetAsync(dnu_acc, 0, (size_t)p->Nb * p->Ng * 4, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    if (velo) {
+      e = cudaMemsetAsync(dnw_acc, 0, (size_t)p->Nx * (2 * p->Hw + 1) * 8, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  if (p->Nc > 0) {
+    CellParams cp{p->phi, p->cf, p->Nb > 0 ? p->batch_id : nullptr, p->cond_id, velo ? p->nu_omega : nullptr,
+                  tab,    p->Nc, p->H, p->Hw, p->Nx, pl.tabw};
+    const int bs = 256;
+    vcb_cell_tables_kernel<<<(unsigned)((p->Nc + bs - 1) / bs), bs, 0, st>>>(cp);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    StreamParams sp{p->S,     velo ? p->U : nullptr, tab,   p->nu,  p->Nb > 0 ? p->dnu : nullptr,
+                    p->shape_inv, p->logbeta,        p->gamma, genepart, cellpart,
+                    dnu_acc,  p->Nc,                 p->Ng, p->ld,  pl.n_split,
+                    p->Nb};
+    dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.n_split);
+    e = launch_stream(p->H, velo, grad, lgi, sp, grid, pl.nthr, pl.smem, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (grad && p->Nc > 0) {
+    CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
+                     dnw_acc,  p->Nc,  pl.n_tiles, pl.NQ,       p->Hw,    velo ? p->Nx : 0};
+    const int bs = 256;
+    const size_t sm = velo ? (size_t)p->Nx * (2 * p->Hw + 1) * 8 : 0;
+    vcb_cell_epilogue_kernel<<<(unsigned)((p->Nc + bs - 1) / bs), bs, sm, st>>>(ce);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    GeneEpiParams ge{};
+    ge.genepart = genepart;
+    ge.shape_inv = p->shape_inv;
+    ge.dnu_acc = grad ? dnu_acc : nullptr;
+    ge.dnw_acc = dnw_acc;
+    ge.spec_S = p->spec_S;
+    ge.spec_U = p->spec_U;
+    ge.lp_S = p->lp_S;
+    ge.lp_U = p->lp_U;
+    ge.d_nu = p->d_nu;
+    ge.d_dnu = p->d_dnu;
+    ge.d_shape_inv = p->d_shape_inv;
+    ge.d_logbeta = p->d_logbeta;
+    ge.d_gamma = p->d_gamma;
+    ge.d_nu_omega = p->d_nu_omega;
+    ge.Nc = p->Nc;
+    ge.Ng = p->Ng;
+    ge.ld = p->ld;
+    ge.n_split = pl.n_split;
+    ge.H = p->H;
+    ge.Nb = p->Nb;
+    ge.Nx = p->Nx;
+    ge.Hw = p->Hw;
+    ge.velo = velo;
+    ge.grad = grad;
+    ge.lginline = lgi;
+    vcb_gene_epilogue_kernel<<<(unsigned)((p->Ng + kEpiGenes - 1) / kEpiGenes), kEpiGenes * kEpiLanes, 0, st>>>(ge);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return VCB_OK;
+}
+
+}  // namespace vcb
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+extern "C" {
+
+int vcb_version(void) { return VCB_VERSION; }
+
+const char* vcb_strerror(int code) {
+  switch (code) {
+    case VCB_OK: return "ok";
+    case VCB_ERR_NULL: return "vcb: a required pointer is NULL";
+    case VCB_ERR_SIZE: return "vcb: a size argument is out of range";
+    case VCB_ERR_ALIGN: return "vcb: ld must be a multiple of 4 and S/U/workspace 16-byte aligned";
+    case VCB_ERR_HARMONICS: return "vcb: number of harmonics above VCB_MAX_HARMONICS";
+    case VCB_ERR_WORKSPACE: return "vcb: workspace smaller than vcb_workspace_bytes()";
+    case VCB_ERR_SPECTRUM: return "vcb: count spectrum missing (or pass VCB_FLAG_LGAMMA_INLINE)";
+    case VCB_ERR_DEVICE: return "vcb: no sm_100 CUDA device";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "vcb: unknown error";
+}
+
+size_t vcb_workspace_bytes(const vcb_problem_t* p) {
+  if (p == nullptr || p->Ng <= 0 || p->ld < p->Ng || p->Nc < 0 || p->H < 0 || p->H > VCB_MAX_HARMONICS || p->Hw < 0 ||
+      p->Hw > VCB_MAX_HARMONICS)
+    return 0;
+  return vcb::make_plan(p, p->U != nullptr).total;
+}
+
+int vcb_phase_fwd_bwd(const vcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
+  return vcb::run(p, false, workspace, workspace_bytes, stream);
+}
+
+int vcb_velocity_fwd_bwd(const vcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
+  return vcb::run(p, true, workspace, workspace_bytes, stream);
+}
+
+int vcb_count_histogram(const float* M, int64_t Nc, int64_t Ng, int64_t ld, int32_t B, uint32_t* hist, int32_t* status,
+                        void* stream) {
+  if (!M || !hist || !status) return VCB_ERR_NULL;
+  if (Nc < 0 || Ng <= 0 || ld < Ng || B < 2) return VCB_ERR_SIZE;
+  if (Nc == 0) return VCB_OK;
+  const int bs = 128;
+  const int cells_per_block = 512;
+  dim3 grid((unsigned)((Ng + bs - 1) / bs), (unsigned)((Nc + cells_per_block - 1) / cells_per_block));
+  vcb::vcb_count_histogram_kernel<<<grid, bs, 0, (cudaStream_t)stream>>>(M, Nc, Ng, ld, B, hist, status,
+                                                                        cells_per_block);
+  return (int)cudaGetLastError();
+}
+
+int vcb_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_dev,
+                     float lr0, float lrd, float beta1, float beta2, float eps, float clip, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step_dev) return VCB_ERR_NULL;
+  if (n < 0) return VCB_ERR_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  vcb::vcb_adam_tick_kernel<<<1, 1, 0, st>>>((long long*)step_dev);
+  if (n > 0) {
+    const int bs = 256;
+    long long blocks = (n + bs - 1) / bs;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    vcb::vcb_clipped_adam_kernel<<<(unsigned)blocks, bs, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n,
+                                                                 (const long long*)step_dev, lr0, lrd, beta1, beta2,
+                                                                 eps, clip);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,306 @@
+"""Host side of the fused ELBO+gradient op: packed device-resident counts, the raw C-ABI call and the
+``torch.autograd.Function`` the model functions use.
+
+Replaces, for the negative-binomial noise model, the (Ng,Nc) op chain of
+``velocycle/phase_inference_model.py:368-393`` and ``velocycle/velocity_inference_model.py:344-386``
+(Fourier basis -> ElogS/ElogU einsums -> ``GammaPoisson.log_prob`` -> autograd backward).
+PyTorch is plumbing here (device memory, streams, autograd wiring); the arithmetic lives in
+``csrc/`` behind ``include/vcb.h``.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import VcbProblem, VcbSpectrum, VCB_FLAG_GRAD, VCB_FLAG_LGAMMA_INLINE
+
+__all__ = ["CountSpectrum", "PackedCounts", "fused_elbo_grad", "FusedCycleNB", "fused_cycle_nb"]
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.VcbError(f"{name} must be a CUDA tensor: velocycle_b200 has no CPU path")
+    return t.detach().to(torch.float32).contiguous()
+
+
+@dataclass
+class CountSpectrum:
+    """Per-gene histogram of one count matrix in CSR form (built once per dataset).
+
+    ``lgamma(r+k) - lgamma(r) - lgamma(k+1)`` and ``digamma(r+k) - digamma(r)`` depend on the data only
+    through how often each count value k occurs in a gene, so their sums over cells are evaluated per
+    step from this spectrum (a few hundred thousand terms) instead of per cell and gene (billions).
+    """
+
+    off: torch.Tensor  # int32 [Ng+1]
+    val: torch.Tensor  # float32 [nnz] distinct k > 0
+    mult: torch.Tensor  # float32 [nnz] how many cells show that k
+    lgk1: torch.Tensor  # float64 [Ng]  sum_c lgamma(k+1)
+    max_count: int
+
+    def as_struct(self) -> VcbSpectrum:
+        return VcbSpectrum(self.off.data_ptr(), self.val.data_ptr(), self.mult.data_ptr(), self.lgk1.data_ptr())
+
+    @staticmethod
+    def build(M: torch.Tensor, Nc: int, Ng: int, ld: int) -> "CountSpectrum":
+        """M: (Nc, ld) float32 CUDA, cell-major.  Raises on negative or non-integer counts."""
+        lib = _lib.load()
+        dev = M.device
+        kmax = int(M.max().item()) if Nc > 0 else 0
+        if kmax >= (1 << 20):
+            raise _lib.VcbError(f"count value {kmax} too large for the histogram path; use inline=True")
+        B = kmax + 2
+        hist = torch.zeros((Ng, B), dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(
+            lib.vcb_count_histogram(M.data_ptr(), Nc, Ng, ld, B, hist.data_ptr(), status.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream),
+            "vcb_count_histogram",
+        )
+        if int(status.item()) != 0:
+            raise _lib.VcbError(
+                "counts must be non-negative integers (GammaPoisson.support, as Pyro's validation "
+                "enforces for the reference); pass inline=True for real-valued pseudo-counts"
+            )
+        h = hist[:, 1:]  # k = 0 contributes nothing
+        nz = (h > 0)
+        per_gene = nz.sum(1)
+        off = torch.zeros(Ng + 1, dtype=torch.int32, device=dev)
+        off[1:] = per_gene.cumsum(0).to(torch.int32)
+        idx = nz.nonzero(as_tuple=False)  # row-major: sorted by gene then k
+        val = (idx[:, 1] + 1).to(torch.float32)
+        mult = h[nz].to(torch.float32)
+        ks = torch.arange(B, device=dev, dtype=torch.float64)
+        lgk1 = (hist.to(torch.float64) * torch.lgamma(ks + 1.0)).sum(1)
+        if val.numel() == 0:  # keep valid device pointers
+            val = torch.zeros(1, dtype=torch.float32, device=dev)
+            mult = torch.zeros(1, dtype=torch.float32, device=dev)
+        return CountSpectrum(off.contiguous(), val.contiguous(), mult.contiguous(), lgk1.contiguous(), kmax)
+
+
+class PackedCounts:
+    """Device-resident spliced / unspliced counts in the layout the kernels stream.
+
+    Cell-major float32 ``[Nc][ld]`` with ``ld = roundup(Ng, 4)`` (16-byte rows for 128-bit loads and
+    TMA bulk copies), zero padding columns, int32 batch / condition ids, and the count spectra.
+    ``from_model_tensors`` accepts the reference's ``mp.S`` / ``mp.U`` (logical (Ng,Nc), physically
+    cell-major, ``preprocessing.py:193-194``) and the one-hot design tensors ``mp.Db`` / ``mp.D``.
+    """
+
+    def __init__(self, S: torch.Tensor, U: Optional[torch.Tensor], Ng: int,
+                 batch_id: Optional[torch.Tensor] = None, cond_id: Optional[torch.Tensor] = None,
+                 spectrum: bool = True):
+        if not S.is_cuda:
+            raise _lib.VcbError("PackedCounts needs CUDA tensors: velocycle_b200 has no CPU path")
+        assert S.dim() == 2 and S.dtype == torch.float32 and S.is_contiguous()
+        self.Nc, self.ld = int(S.shape[0]), int(S.shape[1])
+        self.Ng = int(Ng)
+        assert self.ld % 4 == 0 and self.ld >= self.Ng
+        assert S.data_ptr() % 16 == 0
+        self.S, self.U = S, U
+        if U is not None:
+            assert U.shape == S.shape and U.dtype == torch.float32 and U.is_contiguous() and U.data_ptr() % 16 == 0
+        dev = S.device
+        self.batch_id = None if batch_id is None else batch_id.to(device=dev, dtype=torch.int32).contiguous()
+        self.cond_id = None if cond_id is None else cond_id.to(device=dev, dtype=torch.int32).contiguous()
+        self.spec_S = self.spec_U = None
+        if spectrum:
+            self.build_spectra()
+
+    def build_spectra(self) -> None:
+        if self.spec_S is None:
+            self.spec_S = CountSpectrum.build(self.S, self.Nc, self.Ng, self.ld)
+        if self.U is not None and self.spec_U is None:
+            self.spec_U = CountSpectrum.build(self.U, self.Nc, self.Ng, self.ld)
+
+    @property
+    def device(self):
+        return self.S.device
+
+    @staticmethod
+    def pack_matrix(M: torch.Tensor, layout: str = "genes_by_cells") -> torch.Tensor:
+        """Return a (Nc, roundup(Ng,4)) float32 contiguous copy.  ``layout`` names the LOGICAL shape of M."""
+        if layout == "genes_by_cells":
+            M = M.T  # logical (Nc, Ng); for the reference's mp.S this is the physical layout already
+        elif layout != "cells_by_genes":
+            raise ValueError(f"{layout=}")
+        Nc, Ng = M.shape
+        ld = (Ng + 3) // 4 * 4
+        out = torch.zeros((Nc, ld), dtype=torch.float32, device=M.device)
+        out[:, :Ng] = M
+        return out
+
+    @staticmethod
+    def one_hot_to_ids(D: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """mp.Db (Nb,1,Nc) / (Nb,1,1,1,Nc) or mp.D (Nx,1,1,Nc) one-hot -> int32 ids (Nc,)."""
+        if D is None:
+            return None
+        D2 = D.reshape(D.shape[0], -1)
+        return D2.argmax(0).to(torch.int32)
+
+    @classmethod
+    def from_model_tensors(cls, S, U=None, Db=None, D=None, spectrum: bool = True) -> "PackedCounts":
+        Ng = int(S.shape[0])
+        Sp = cls.pack_matrix(S)
+        Up = None if U is None else cls.pack_matrix(U)
+        return cls(Sp, Up, Ng, cls.one_hot_to_ids(Db), cls.one_hot_to_ids(D), spectrum=spectrum)
+
+
+def fused_elbo_grad(
+    counts: PackedCounts,
+    phi: torch.Tensor,
+    cf: Optional[torch.Tensor],
+    nu: torch.Tensor,
+    dnu: Optional[torch.Tensor],
+    shape_inv: torch.Tensor,
+    logbeta: Optional[torch.Tensor] = None,
+    gamma: Optional[torch.Tensor] = None,
+    nu_omega: Optional[torch.Tensor] = None,
+    grad: bool = True,
+    inline_lgamma: bool = False,
+    want_d_omega: bool = False,
+) -> Dict[str, torch.Tensor]:
+    """One launch sequence of the fused path through the C ABI.  All tensors float32 CUDA.
+
+    velocity model iff ``nu_omega`` is given.  Returns ``lp_S`` [Ng] (``lp_U``) and, under ``grad``, the
+    gradients of ``sum(lp_S) + sum(lp_U)`` keyed like ``include/vcb.h``.
+    """
+    lib = _lib.load()
+    dev = counts.device
+    velocity = nu_omega is not None
+    Nc, Ng, ld = counts.Nc, counts.Ng, counts.ld
+    phi = _dev_f32(phi, "phi").reshape(-1)
+    nu = _dev_f32(nu, "nu").reshape(Ng, -1)
+    K = nu.shape[1]
+    shape_inv = _dev_f32(shape_inv, "shape_inv").reshape(-1)
+    cf = None if cf is None else _dev_f32(cf, "cf").reshape(-1)
+    assert phi.numel() == Nc and shape_inv.numel() == Ng and K % 2 == 1
+    Nb = 0
+    if dnu is not None:
+        dnu = _dev_f32(dnu, "dnu").reshape(-1, Ng)
+        Nb = dnu.shape[0]
+        if counts.batch_id is None:
+            if Nb != 1:
+                raise _lib.VcbError("dnu with more than one batch needs batch ids")
+            counts.batch_id = torch.zeros(Nc, dtype=torch.int32, device=dev)
+    p = VcbProblem()
+    p.Nc, p.Ng, p.ld = Nc, Ng, ld
+    p.H, p.Nb = (K - 1) // 2, Nb
+    p.flags = (VCB_FLAG_GRAD if grad else 0) | (VCB_FLAG_LGAMMA_INLINE if inline_lgamma else 0)
+    p.S = counts.S.data_ptr()
+    p.phi, p.cf = phi.data_ptr(), _ptr(cf)
+    p.batch_id = _ptr(counts.batch_id) if Nb > 0 else None
+    p.nu, p.dnu, p.shape_inv = nu.data_ptr(), _ptr(dnu), shape_inv.data_ptr()
+    out: Dict[str, torch.Tensor] = {}
+    f32 = dict(dtype=torch.float32, device=dev)
+    out["lp_S"] = torch.empty(Ng, **f32)
+    p.lp_S = out["lp_S"].data_ptr()
+    if velocity:
+        if counts.U is None:
+            raise _lib.VcbError("velocity model needs unspliced counts")
+        logbeta = _dev_f32(logbeta, "logbeta").reshape(-1)
+        gamma = _dev_f32(gamma, "gamma").reshape(-1)
+        nu_omega = _dev_f32(nu_omega, "nu_omega")
+        nu_omega = nu_omega.reshape(nu_omega.shape[0], -1)
+        Nx, Kw = nu_omega.shape
+        if Nx > 1 and counts.cond_id is None:
+            raise _lib.VcbError("more than one condition needs condition ids")
+        p.Hw, p.Nx = (Kw - 1) // 2, Nx
+        p.U = counts.U.data_ptr()
+        p.cond_id = _ptr(counts.cond_id)
+        p.logbeta, p.gamma, p.nu_omega = logbeta.data_ptr(), gamma.data_ptr(), nu_omega.data_ptr()
+        out["lp_U"] = torch.empty(Ng, **f32)
+        p.lp_U = out["lp_U"].data_ptr()
+    else:
+        p.Hw, p.Nx = 0, 0
+    if not inline_lgamma:
+        counts.build_spectra()
+        p.spec_S = counts.spec_S.as_struct()
+        if velocity:
+            p.spec_U = counts.spec_U.as_struct()
+    if grad:
+        out["d_nu"] = torch.empty(Ng, K, **f32)
+        out["d_shape_inv"] = torch.empty(Ng, **f32)
+        out["d_phi"] = torch.empty(Nc, **f32)
+        out["d_cf"] = torch.empty(Nc, **f32)
+        p.d_nu, p.d_shape_inv = out["d_nu"].data_ptr(), out["d_shape_inv"].data_ptr()
+        p.d_phi, p.d_cf = out["d_phi"].data_ptr(), out["d_cf"].data_ptr()
+        if Nb > 0:
+            out["d_dnu"] = torch.empty(Nb, Ng, **f32)
+            p.d_dnu = out["d_dnu"].data_ptr()
+        if velocity:
+            out["d_logbeta"] = torch.empty(Ng, **f32)
+            out["d_gamma"] = torch.empty(Ng, **f32)
+            out["d_nu_omega"] = torch.empty(Nx, Kw, **f32)
+            p.d_logbeta, p.d_gamma = out["d_logbeta"].data_ptr(), out["d_gamma"].data_ptr()
+            p.d_nu_omega = out["d_nu_omega"].data_ptr()
+            if want_d_omega:
+                out["d_omega"] = torch.empty(Nc, **f32)
+                p.d_omega = out["d_omega"].data_ptr()
+    ws_bytes = lib.vcb_workspace_bytes(C.byref(p))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    fn = lib.vcb_velocity_fwd_bwd if velocity else lib.vcb_phase_fwd_bwd
+    _lib.check(fn(C.byref(p), ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream),
+               "vcb_velocity_fwd_bwd" if velocity else "vcb_phase_fwd_bwd")
+    out["_workspace"] = ws  # keep alive until the stream has consumed it
+    return out
+
+
+class FusedCycleNB(torch.autograd.Function):
+    """log-likelihood of the count matrices as an autograd node with a fused forward+backward.
+
+    ``forward`` returns the per-gene log-prob sums (lp_S, lp_U) and computes every gradient in the same
+    streaming pass; ``backward`` only scales the saved gradients.  That is exact when all genes of both
+    sites carry the same upstream weight, which is what ``Trace_ELBO`` produces (-1 for every site).
+    Any other weighting poisons the result with NaN instead of returning a silently wrong gradient.
+    """
+
+    @staticmethod
+    def forward(ctx, counts, inline_lgamma, phi, cf, nu, dnu, shape_inv, logbeta, gamma, nu_omega):
+        velocity = nu_omega is not None
+        needs = ctx.needs_input_grad[2:]
+        grad = any(needs)
+        out = fused_elbo_grad(counts, phi, cf, nu, dnu, shape_inv, logbeta, gamma, nu_omega,
+                              grad=grad, inline_lgamma=inline_lgamma)
+        ctx.velocity = velocity
+        ctx.grad_computed = grad
+        ctx.shapes = [None if t is None else t.shape for t in (phi, cf, nu, dnu, shape_inv, logbeta, gamma, nu_omega)]
+        if grad:
+            names = ["d_phi", "d_cf", "d_nu", "d_dnu", "d_shape_inv", "d_logbeta", "d_gamma", "d_nu_omega"]
+            ctx.save_for_backward(*[out.get(n) if out.get(n) is not None else torch.empty(0, device=counts.device)
+                                    for n in names])
+        lpS = out["lp_S"]
+        lpU = out["lp_U"] if velocity else torch.zeros_like(lpS)
+        return lpS, lpU
+
+    @staticmethod
+    def backward(ctx, g_lpS, g_lpU):
+        if not ctx.grad_computed:
+            return (None,) * 10
+        saved = ctx.saved_tensors
+        s = g_lpS.reshape(-1)[0]
+        bad = (g_lpS != s).any()
+        if ctx.velocity:
+            bad = bad | (g_lpU != s).any()
+        scale = torch.where(bad, torch.full_like(s, float("nan")), s)
+        grads = []
+        for i, (t, shp) in enumerate(zip(saved, ctx.shapes)):
+            if shp is None or t.numel() == 0 or not ctx.needs_input_grad[2 + i]:
+                grads.append(None)
+            else:
+                grads.append((t * scale).reshape(shp))
+        return (None, None, *grads)
+
+
+def fused_cycle_nb(counts: PackedCounts, phi, cf, nu, dnu, shape_inv, logbeta=None, gamma=None, nu_omega=None,
+                   inline_lgamma: bool = False):
+    """Functional wrapper: returns (lp_S[Ng], lp_U[Ng])."""
+    return FusedCycleNB.apply(counts, inline_lgamma, phi, cf, nu, dnu, shape_inv, logbeta, gamma, nu_omega)
