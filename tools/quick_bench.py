@@ -27,9 +27,9 @@ def run(Nc, Ng, velocity=True, H=3, iters=5, inline=False, Nb=1, Nx=1):
           f"maxk={counts.spec_S.max_count if counts.spec_S else -1}", flush=True)
 
 if __name__ == "__main__":
+    print("VCB_PAIRS_PER_THREAD =", os.environ.get("VCB_PAIRS_PER_THREAD"))
     run(100_000, 2000, True)
     run(100_000, 2000, False)
-    run(100_000, 2000, True, inline=True)
     run(400_000, 2000, True)
     run(100_000, 5000, True, Nb=16, Nx=2)
     run(3000, 218, True, H=1)

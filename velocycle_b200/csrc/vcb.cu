@@ -5,15 +5,20 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "vcb_common.cuh"
 #include "vcb_stream.cuh"
+
+#ifndef VCB_DEFAULT_NP
+#define VCB_DEFAULT_NP 1
+#endif
 
 namespace vcb {
 
 // ======================================================================================================
 // Per-cell prologue: Fourier tables.  One thread per cell.
-//   row = [zeta_1..zeta_2H | zeta'_1..zeta'_2H | zeta''_1..zeta''_2H | omega | cf | batch | pad]
+//   row = pairs {z,z} of [zeta_1..zeta_2H | zeta'_1..zeta'_2H | zeta''_1..zeta''_2H | omega | cf], then batch | pad
 // Column order [sin, cos] per harmonic and sin(fl(n*phi)) follow utils.py:420-435.
 // ======================================================================================================
 struct CellParams {
@@ -33,16 +38,20 @@ __global__ void vcb_cell_tables_kernel(const CellParams P) {
   const float phi = P.phi[c];
   float* row = P.tab + c * P.tabw;
   const int H = P.H;
+  auto put = [&](int pair, float v) {  // every entry twice: a broadcast LDS.128 then yields {z,z} operands
+    row[2 * pair] = v;
+    row[2 * pair + 1] = v;
+  };
   for (int n = 1; n <= H; ++n) {
     float s, co;
     const float fn = (float)n;
     sincosf(fn * phi, &s, &co);
-    row[2 * n - 2] = s;
-    row[2 * n - 1] = co;
-    row[2 * H + 2 * n - 2] = fn * co;
-    row[2 * H + 2 * n - 1] = -fn * s;
-    row[4 * H + 2 * n - 2] = -fn * fn * s;
-    row[4 * H + 2 * n - 1] = -fn * fn * co;
+    put(2 * n - 2, s);
+    put(2 * n - 1, co);
+    put(2 * H + 2 * n - 2, fn * co);
+    put(2 * H + 2 * n - 1, -fn * s);
+    put(4 * H + 2 * n - 2, -fn * fn * s);
+    put(4 * H + 2 * n - 1, -fn * fn * co);
   }
   float omega = 0.f;
   if (P.nu_omega != nullptr) {
@@ -57,17 +66,17 @@ __global__ void vcb_cell_tables_kernel(const CellParams P) {
       omega = fmaf(nw[2 * n], co, omega);
     }
   }
-  row[6 * H] = omega;
-  row[6 * H + 1] = P.cf ? P.cf[c] : 0.f;
-  row[6 * H + 2] = __int_as_float(P.batch_id ? P.batch_id[c] : 0);
-  for (int i = 6 * H + 3; i < P.tabw; ++i) row[i] = 0.f;
+  put(6 * H, omega);
+  put(6 * H + 1, P.cf ? P.cf[c] : 0.f);
+  row[12 * H + 4] = __int_as_float(P.batch_id ? P.batch_id[c] : 0);
+  for (int i = 12 * H + 5; i < P.tabw; ++i) row[i] = 0.f;
 }
 
 // ======================================================================================================
 // Per-cell epilogue: sum the gene-tile partials, add the omega(phi) path to d/dphi, reduce d/dnu_omega.
 // ======================================================================================================
 struct CellEpiParams {
-  const float* cellpart;  // [n_tiles][NQ][Nc]
+  const float* cellpart;  // [n_part][Nc][NQ], n_part = gene tiles x warps per CTA
   const float* phi;
   const int32_t* cond_id;
   const float* nu_omega;
@@ -76,7 +85,7 @@ struct CellEpiParams {
   float* d_omega;
   double* dnw_acc;  // [Nx*Kw], zeroed
   long long Nc;
-  int n_tiles, NQ, Hw, Nx;
+  int n_part, NQ, Hw, Nx;
 };
 
 __global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
@@ -89,8 +98,8 @@ __global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (c < P.Nc) {
     float q[3] = {0.f, 0.f, 0.f};
-    for (int t = 0; t < P.n_tiles; ++t)
-      for (int i = 0; i < P.NQ; ++i) q[i] += P.cellpart[((long long)t * P.NQ + i) * P.Nc + c];
+    for (int t = 0; t < P.n_part; ++t)
+      for (int i = 0; i < P.NQ; ++i) q[i] += P.cellpart[((long long)t * P.Nc + c) * P.NQ + i];
     float dphi = q[1];
     if (velo) {
       const float phi = P.phi[c];
@@ -203,16 +212,15 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
       if (P.spec_S.lgk1) lgS -= P.spec_S.lgk1[g];
       if (P.velo && P.spec_U.lgk1) lgU -= P.spec_U.lgk1[g];
     }
-    const double n = (double)P.Nc;
-    const double lnr = log(r);
+    // the streaming kernel works in units of mu/r: LS = sum lg2(1 + mu/r), so n r log r has already cancelled
     const double AS = s_rows[ROW_AS][gx] * kLn2d, LS = s_rows[ROW_LS][gx] * kLn2d;
-    const double lpS = AS - r * LS + n * r * lnr + lgS;
+    const double lpS = AS - r * LS + lgS;
     P.lp_S[g] = (float)lpS;
     double LU = 0.0;
     if (P.velo) {
       const double AU = s_rows[ROW_AU][gx] * kLn2d;
       LU = s_rows[ROW_LU][gx] * kLn2d;
-      P.lp_U[g] = (float)(AU - r * LU + n * r * lnr + lgU);
+      P.lp_U[g] = (float)(AU - r * LU + lgU);
     }
     if (P.grad) {
       double dnu0 = s_rows[ROW_DNU][gx];
@@ -229,8 +237,7 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
         for (int k = 1; k < K; ++k) P.d_nu[g * K + k] = (float)s_rows[ROW_DNU + k][gx];
       }
       const double psi = P.lginline ? s_rows[ROW_PSI][gx] : (psS + psU);
-      const double nmat = P.velo ? 2.0 : 1.0;
-      const double dr = psi + nmat * n * lnr - (LS + LU) - dnu0 / r;
+      const double dr = psi - (LS + LU) - dnu0 / r;
       if (P.d_shape_inv) P.d_shape_inv[g] = (float)(-r * r * dr);
       if (P.velo) {
         if (P.d_logbeta) P.d_logbeta[g] = (float)(-s_rows[ROW_GU][gx]);
@@ -301,7 +308,7 @@ __global__ void vcb_clipped_adam_kernel(float* __restrict__ p, const float* __re
 // Host side
 // ======================================================================================================
 struct Plan {
-  int nthr, tile_g, n_tiles, n_split, W_max;
+  int np, nthr, tile_g, n_tiles, n_split, W_max;
   int tabw, rows, NQ;
   size_t off_tab, off_genepart, off_cellpart, off_dnuacc, off_dnwacc, total;
   int smem;
@@ -322,26 +329,38 @@ static int sm_count() {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static int pairs_per_thread() {
+  // NP = 1: 512 threads x 2 genes (16 warps/SM, <=128 regs); NP = 2: 256 threads x 4 genes (8 warps/SM, <=255 regs)
+  static int np = 0;
+  if (np == 0) {
+    const char* e = getenv("VCB_PAIRS_PER_THREAD");
+    np = (e && e[0] == '2') ? 2 : ((e && e[0] == '1') ? 1 : VCB_DEFAULT_NP);
+  }
+  return np;
+}
+
 static Plan make_plan(const vcb_problem_t* p, bool velo) {
   Plan pl{};
   const bool grad = (p->flags & VCB_FLAG_GRAD) != 0;
+  pl.np = pairs_per_thread();
+  const int gpt = 2 * pl.np;
+  const int tmax = max_threads(pl.np);
   // threads per CTA: the widest tile that wastes the fewest lanes
-  const int cand[5] = {512, 256, 128, 64, 32};
   double best = -1.0;
-  for (int i = 0; i < 5; ++i) {
-    const long long tg = 4LL * cand[i];
+  for (int t = tmax; t >= 32; t >>= 1) {
+    const long long tg = (long long)gpt * t;
     const long long nt = (p->ld + tg - 1) / tg;
     const double eff = (double)p->ld / (double)(nt * tg);
     if (eff > best + 0.02) {
       best = eff;
-      pl.nthr = cand[i];
+      pl.nthr = t;
     }
   }
-  pl.tile_g = 4 * pl.nthr;
+  pl.tile_g = gpt * pl.nthr;
   pl.n_tiles = (int)((p->ld + pl.tile_g - 1) / pl.tile_g);
   if (pl.n_tiles < 1) pl.n_tiles = 1;
   pl.W_max = (int)(p->ld < pl.tile_g ? p->ld : pl.tile_g);
-  const int ctas_per_sm = kMaxThreads / pl.nthr;
+  const int ctas_per_sm = tmax / pl.nthr;
   long long ns = ((long long)sm_count() * ctas_per_sm) / pl.n_tiles;
   const long long max_split = (p->Nc + kCellsPerStage - 1) / kCellsPerStage;
   if (ns > max_split) ns = max_split;
@@ -357,7 +376,7 @@ static Plan make_plan(const vcb_problem_t* p, bool velo) {
   pl.off_genepart = off;
   off = align_up(off + (size_t)pl.n_split * pl.rows * p->ld * 4, 256);
   pl.off_cellpart = off;
-  off = align_up(off + (size_t)pl.n_tiles * pl.NQ * p->Nc * 4, 256);
+  off = align_up(off + (size_t)pl.n_tiles * (pl.nthr / 32) * pl.NQ * p->Nc * 4, 256);
   pl.off_dnuacc = off;
   off = align_up(off + (size_t)(p->Nb > 0 ? p->Nb : 0) * p->Ng * 4, 256);
   pl.off_dnwacc = off;
@@ -389,43 +408,27 @@ static int validate(const vcb_problem_t* p, bool velo) {
   return VCB_OK;
 }
 
-template <int H, bool VELO, bool GRAD, bool LGI>
-static cudaError_t launch_stream_t(const StreamParams& sp, dim3 grid, int nthr, int smem, cudaStream_t st) {
-  auto kfn = vcb_stream_kernel<H, VELO, GRAD, LGI>;
-  static int configured_smem = 0;  // per instantiation; raising the opt-in limit is idempotent
-  if (smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured_smem = smem;
-  }
-  kfn<<<grid, nthr, smem, st>>>(sp);
-  return cudaGetLastError();
-}
+// one translation unit per H (vcb_stream_inst.cu, compiled with -DVCB_INST_H=h) so the build parallelises
+#define VCB_DECL_LAUNCH(h)                                                                                     \
+  cudaError_t vcb_launch_stream_h##h(bool velo, bool grad, bool lgi, int np, const StreamParams& sp, dim3 grid, \
+                                     int nthr, int smem, cudaStream_t st);
+VCB_DECL_LAUNCH(0)
+VCB_DECL_LAUNCH(1)
+VCB_DECL_LAUNCH(2)
+VCB_DECL_LAUNCH(3)
+VCB_DECL_LAUNCH(4)
+VCB_DECL_LAUNCH(5)
+#undef VCB_DECL_LAUNCH
 
-template <int H>
-static cudaError_t launch_stream_h(bool velo, bool grad, bool lgi, const StreamParams& sp, dim3 grid, int nthr,
-                                   int smem, cudaStream_t st) {
-  if (velo) {
-    if (grad) return lgi ? launch_stream_t<H, true, true, true>(sp, grid, nthr, smem, st)
-                         : launch_stream_t<H, true, true, false>(sp, grid, nthr, smem, st);
-    return lgi ? launch_stream_t<H, true, false, true>(sp, grid, nthr, smem, st)
-               : launch_stream_t<H, true, false, false>(sp, grid, nthr, smem, st);
-  }
-  if (grad) return lgi ? launch_stream_t<H, false, true, true>(sp, grid, nthr, smem, st)
-                       : launch_stream_t<H, false, true, false>(sp, grid, nthr, smem, st);
-  return lgi ? launch_stream_t<H, false, false, true>(sp, grid, nthr, smem, st)
-             : launch_stream_t<H, false, false, false>(sp, grid, nthr, smem, st);
-}
-
-static cudaError_t launch_stream(int H, bool velo, bool grad, bool lgi, const StreamParams& sp, dim3 grid, int nthr,
-                                 int smem, cudaStream_t st) {
+static cudaError_t launch_stream(int H, bool velo, bool grad, bool lgi, int np, const StreamParams& sp, dim3 grid,
+                                 int nthr, int smem, cudaStream_t st) {
   switch (H) {
-    case 0: return launch_stream_h<0>(velo, grad, lgi, sp, grid, nthr, smem, st);
-    case 1: return launch_stream_h<1>(velo, grad, lgi, sp, grid, nthr, smem, st);
-    case 2: return launch_stream_h<2>(velo, grad, lgi, sp, grid, nthr, smem, st);
-    case 3: return launch_stream_h<3>(velo, grad, lgi, sp, grid, nthr, smem, st);
-    case 4: return launch_stream_h<4>(velo, grad, lgi, sp, grid, nthr, smem, st);
-    case 5: return launch_stream_h<5>(velo, grad, lgi, sp, grid, nthr, smem, st);
+    case 0: return vcb_launch_stream_h0(velo, grad, lgi, np, sp, grid, nthr, smem, st);
+    case 1: return vcb_launch_stream_h1(velo, grad, lgi, np, sp, grid, nthr, smem, st);
+    case 2: return vcb_launch_stream_h2(velo, grad, lgi, np, sp, grid, nthr, smem, st);
+    case 3: return vcb_launch_stream_h3(velo, grad, lgi, np, sp, grid, nthr, smem, st);
+    case 4: return vcb_launch_stream_h4(velo, grad, lgi, np, sp, grid, nthr, smem, st);
+    case 5: return vcb_launch_stream_h5(velo, grad, lgi, np, sp, grid, nthr, smem, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -470,14 +473,14 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
     StreamParams sp{p->S,     velo ? p->U : nullptr, tab,   p->nu,  p->Nb > 0 ? p->dnu : nullptr,
                     p->shape_inv, p->logbeta,        p->gamma, genepart, cellpart,
                     dnu_acc,  p->Nc,                 p->Ng, p->ld,  pl.n_split,
-                    p->Nb};
+                    p->Nb, getenv("VCB_DEBUG_SKIP_COMPUTE") != nullptr ? 1 : 0};
     dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.n_split);
-    e = launch_stream(p->H, velo, grad, lgi, sp, grid, pl.nthr, pl.smem, st);
+    e = launch_stream(p->H, velo, grad, lgi, pl.np, sp, grid, pl.nthr, pl.smem, st);
     if (e != cudaSuccess) return (int)e;
   }
   if (grad && p->Nc > 0) {
     CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
-                     dnw_acc,  p->Nc,  pl.n_tiles, pl.NQ,       p->Hw,    velo ? p->Nx : 0};
+                     dnw_acc,  p->Nc,  pl.n_tiles * (pl.nthr / 32), pl.NQ, p->Hw, velo ? p->Nx : 0};
     const int bs = 256;
     const size_t sm = velo ? (size_t)p->Nx * (2 * p->Hw + 1) * 8 : 0;
     vcb_cell_epilogue_kernel<<<(unsigned)((p->Nc + bs - 1) / bs), bs, sm, st>>>(ce);
