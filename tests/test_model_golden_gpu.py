@@ -1,0 +1,105 @@
+"""GPU: the drop-in model functions (fused CUDA likelihood) against (a) the golden vectors produced by the
+reference's own model source and (b) whole SVI trajectories of the unfused restatement under the same RNG."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_golden_cpu import CASES, KINDS, load, section
+
+pytestmark = pytest.mark.gpu
+
+
+def _mp(inp, kind, device="cuda"):
+    from velocycle_b200.preprocessing import make_phase_metaparams, make_velocity_metaparams
+
+    common = dict(batch_id=inp["batch_id"], Nb=int(inp["Nb"]), count_factor=inp["cf"], device=device)
+    if kind.startswith("phase"):
+        return make_phase_metaparams(inp["S"], inp["U"], inp["mu_nu"], inp["sd_nu"], inp["phixy_prior"],
+                                     with_delta_nu=(kind == "phase"), **common)
+    return make_velocity_metaparams(inp["S"], inp["U"], inp["mu_nu"], inp["sd_nu"], inp["phixy_prior"],
+                                    inp["mu_nw"], inp["sd_nw"], cond_id=inp["cond_id"], Nx=int(inp["Nx"]),
+                                    model_type="lrmn" if kind.endswith("lrmn") else "normal", **common)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("kind", KINDS)
+def test_fused_model_matches_reference_golden(case, kind):
+    from velocycle_b200 import ppl as pyro
+    from velocycle_b200.ppl import poutine
+
+    z, inp = load(case)
+    mp = _mp(inp, kind)
+    draws = {k: v.cuda().requires_grad_(True) for k, v in section(z, kind, "draw").items()}
+    pyro.clear_param_store()
+    tr = poutine.trace(poutine.condition(mp.model_fn, data=draws)).get_trace(mp)
+    tr.compute_log_prob()
+    for site, ref in section(z, kind, "model_lp").items():
+        got = float(tr.nodes[site]["log_prob_sum"])
+        assert abs(got - float(ref)) <= 1e-4 * max(1.0, abs(float(ref))), (site, got, float(ref))
+    total = sum(s["log_prob_sum"] for s in tr.nodes.values() if s["type"] == "sample")
+    assert abs(float(total) - float(z[f"{kind}/model_logjoint"])) <= 1e-4 * abs(float(total))
+    total.backward()
+    for site, ref in section(z, kind, "dlogjoint").items():
+        got = draws[site].grad.cpu().double()
+        err = float((got - ref.double()).abs().max() / (ref.double().abs().max() + 1e-30))
+        # 1e-4, except the relu-kink sites of the wide-prior case (see tests/test_golden_cpu.py): there the fp32
+        # reference itself is 5e-3 away from the fp64 truth
+        kink = kind.startswith("velocity") and site in ("logγg", "ν", "ϕxy", "νω") and case == "case_multi"
+        tol = 2e-2 if kink else (1e-3 if site == "shape_inv" else 1e-4)
+        assert err <= tol, (site, err)
+
+
+def _unfused(kind):
+    from oracle import models
+
+    return {"phase": models.phase_model_unfused, "phase_nodnu": models.phase_model_unfused,
+            "velocity": models.velocity_model_unfused, "velocity_lrmn": models.velocity_model_unfused_lrmn}[kind]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_svi_trajectory_matches_unfused_reference_chain(kind):
+    """Same seed, same device, 25 SVI steps: fused drop-in vs the unfused (Ng,Nc) op chain of the reference.
+    Tolerances (stated): per-step ELBO loss 1e-4 relative; after 25 steps parameters within 2e-3 absolute
+    (phases phixy_locs, speeds nu_omega_locs, gene harmonics nu_locs) -- ClippedAdam's sign-like first steps
+    amplify 1e-6 gradient differences, hence absolute."""
+    from velocycle_b200 import ppl as pyro
+    from velocycle_b200.ppl.infer import SVI, Trace_ELBO
+    from velocycle_b200.ppl.optim import ClippedAdam
+
+    z, inp = load("case_stereo")
+    mp = _mp(inp, kind)
+    runs = {}
+    for name, model in (("fused", mp.model_fn), ("unfused", _unfused(kind))):
+        pyro.clear_param_store()
+        pyro.set_rng_seed(123)
+        svi = SVI(model, mp.guide_fn, ClippedAdam({"lr": 0.03, "lrd": 0.999, "betas": (0.8, 0.99)}), Trace_ELBO())
+        losses = [svi.step(mp) for _ in range(25)]
+        runs[name] = (losses, {k: v.detach().clone() for k, v in pyro.get_param_store().named_parameters()})
+    lf, lu = np.array(runs["fused"][0]), np.array(runs["unfused"][0])
+    assert np.all(np.abs(lf - lu) <= 1e-4 * np.abs(lu)), np.max(np.abs(lf - lu) / np.abs(lu))
+    for name, pu in runs["unfused"][1].items():
+        pf = runs["fused"][1][name]
+        assert float((pf - pu).abs().max()) <= 2e-3, (name, float((pf - pu).abs().max()))
+
+
+def test_conditioned_velocity_fit_driver_runs_and_matches():
+    """The tutorial pattern: condition the velocity model on the phase-stage estimates (phixy, nu, shape_inv, Δν)."""
+    from velocycle_b200 import ppl as pyro
+    from velocycle_b200.ppl.optim import ClippedAdam
+    from velocycle_b200.velocity_inference_model import VelocityFitModel
+
+    z, inp = load("case_stereo")
+    mp = _mp(inp, "velocity_lrmn")
+    draws = section(z, "velocity_lrmn", "draw")
+    cond = {k: draws[k].cuda() for k in ("ϕxy", "ν", "shape_inv", "Δν")}
+    pyro.clear_param_store()
+    pyro.set_rng_seed(5)
+    fit = VelocityFitModel(mp, condition_on=cond, num_samples=4, n_per_bin=2)
+    fit.fit(ClippedAdam({"lr": 0.03, "betas": (0.8, 0.99)}), num_steps=15, verbose=False)
+    assert len(fit.losses) == 15 and np.isfinite(fit.losses).all()
+    assert fit.losses[-1] < fit.losses[0]
+    assert fit.posterior["νω"].shape[0] == 4 and fit.posterior["ω"].shape[-1] == mp.Nc
+    # conditioned sites receive no updates
+    assert torch.equal(pyro.param("ϕxy_locs").detach().cpu(), inp["phixy_prior"].float())

@@ -131,7 +131,7 @@ __global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
 // ======================================================================================================
 // Per-gene epilogue: sum the cell-split partials in fp64, add the parameter-only terms
 // (n r log r, the lgamma / digamma sums over the count spectrum), apply the chain-rule factors.
-// Block = 32 genes x 8 lanes.
+// Block = 8 genes x 32 lanes (the fp64 lgamma/digamma sums over the spectrum want many lanes per gene).
 // ======================================================================================================
 struct GeneEpiParams {
   const float* genepart;  // [n_split][ROWS][ld]
@@ -145,8 +145,8 @@ struct GeneEpiParams {
   int velo, grad, lginline;
 };
 
-constexpr int kEpiGenes = 32;
-constexpr int kEpiLanes = 8;
+constexpr int kEpiGenes = 8;
+constexpr int kEpiLanes = 32;
 constexpr int kEpiMaxRows = ROW_DNU + 2 * VCB_MAX_HARMONICS + 1;
 
 __device__ __forceinline__ void spectrum_sums(const vcb_spectrum_t& sp, long long g, double r, int lane, int nlanes,
@@ -173,17 +173,25 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
   const int ROWS = ROW_DNU + K;
   const bool valid = g < P.Ng;
 
-  for (int row = ly; row < ROWS; row += kEpiLanes) {
-    double s = 0.0;
+  __shared__ double s_part[kEpiLanes][kEpiGenes];
+  for (int row = 0; row < ROWS; ++row) {
     const bool used = (row == ROW_AS || row == ROW_LS) || (P.velo && (row == ROW_AU || row == ROW_LU)) ||
                       (P.velo && P.grad && (row == ROW_GU || row == ROW_W)) || (P.lginline && row == ROW_PSI) ||
                       (P.grad && row >= ROW_DNU);
+    double s = 0.0;
     if (valid && used) {
       const float* src = P.genepart + (long long)row * P.ld + g;
       const long long stride = (long long)ROWS * P.ld;
-      for (int sidx = 0; sidx < P.n_split; ++sidx) s += (double)src[sidx * stride];
+      for (int sidx = ly; sidx < P.n_split; sidx += kEpiLanes) s += (double)src[sidx * stride];
     }
-    s_rows[row][gx] = s;
+    s_part[ly][gx] = s;
+    __syncthreads();
+    if (ly == 0) {  // fixed summation order: deterministic
+      double t = 0.0;
+      for (int l = 0; l < kEpiLanes; ++l) t += s_part[l][gx];
+      s_rows[row][gx] = t;
+    }
+    __syncthreads();
   }
   double r = 1.0;
   if (valid) r = 1.0 / (double)P.shape_inv[g];

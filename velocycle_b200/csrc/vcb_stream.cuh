@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(max_threads(NP), 1) vcb_stream_kernel(const St
   // Synchronisation: no CTA-wide barrier and no warp-to-warp waiting in steady state.
   //   full[s] : TMA bytes of the stage in slot s have landed            (1 arrival + complete_tx)
   //   done[s] : every warp finished reading slot s                      (one arrival per warp)
-  // Refills are work-stolen: every warp polls (once per cell, and while it waits for data) whether the
+  // Refills are work-stolen: every warp polls (twice per stage, and while it waits for data) whether the
   // slot of the next stage to issue has been released, and the warp that wins the CAS on s_next issues
   // the copies.  All warps therefore run identical code and no warp is the designated straggler.
   // (A dedicated producer warp would cost a whole 4-warp register allocation unit: 544 threads are
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(max_threads(NP), 1) vcb_stream_kernel(const St
           pom = pom2.x + pom2.y;
         }
       }
-      poll_refill();
+      if (rr == R / 2 - 1) poll_refill();
       if (GRAD) {
         part[rr * NQ + 0] = pcf;
         part[rr * NQ + 1] = pphi;

@@ -1,0 +1,85 @@
+"""The fused likelihood as seen from a model function: packed-count sidecar lookup and the site distribution.
+
+``pyro.sample("S", FusedCountLikelihood(lp_S, ...), obs=mp.S)`` replaces
+``pyro.sample("S", dist.GammaPoisson(1/shape_inv, 1/(shape_inv*exp(ElogS))), obs=mp.S)``
+(``phase_inference_model.py:391-393``, ``velocity_inference_model.py:383-386``): the site keeps its name and its
+observed value, but its ``log_prob`` is the per-gene sum over cells that the CUDA pass already produced, shape
+(Ng,1) inside the ``genes`` plate -- the (Ng,Nc) matrix of log-probs is never materialised (SURVEY 8b option i).
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch.distributions import constraints
+
+from . import _lib
+from .fused import PackedCounts
+
+__all__ = ["FusedCountLikelihood", "packed_counts_for", "attach_packed_counts"]
+
+_SIDECARS: Dict[Tuple, PackedCounts] = {}
+
+
+def attach_packed_counts(mp, counts: PackedCounts) -> None:
+    """Register ready-made packed counts for ``mp`` (what ``preprocess_for_*`` of this package does)."""
+    _SIDECARS[_key(mp)] = counts
+
+
+def _key(mp) -> Tuple:
+    U = getattr(mp, "U", None)
+    return (mp.S.data_ptr(), tuple(mp.S.shape), 0 if U is None else U.data_ptr(), str(mp.S.device))
+
+
+def packed_counts_for(mp, need_U: bool) -> PackedCounts:
+    """Packed, device-resident counts for a metaparameter tuple; built once per dataset and cached.
+
+    Works for ``mp`` objects made by the reference's own preprocessing: ``mp.S`` / ``mp.U`` logical (Ng,Nc)
+    float tensors, one-hot ``mp.Db`` and ``mp.D``."""
+    pc = getattr(mp, "packed_counts", None)
+    if pc is not None:
+        return pc
+    k = _key(mp)
+    pc = _SIDECARS.get(k)
+    if pc is None or (need_U and pc.U is None):
+        if not mp.S.is_cuda:
+            raise _lib.VcbError(
+                "velocycle_b200 models need mp.S / mp.U on a CUDA device: there is no CPU path "
+                "(pass device=torch.device('cuda') to preprocess_for_*_estimation)"
+            )
+        pc = PackedCounts.from_model_tensors(
+            mp.S, mp.U if need_U else None, getattr(mp, "Db", None), getattr(mp, "D", None) if need_U else None
+        )
+        _SIDECARS[k] = pc
+    return pc
+
+
+class FusedCountLikelihood(torch.distributions.Distribution):
+    """Site distribution whose ``log_prob`` is the precomputed per-gene sum over cells of NB log-pmfs."""
+
+    arg_constraints: dict = {}
+    support = constraints.nonnegative_integer
+    has_rsample = False
+
+    def __init__(self, log_prob_per_gene: torch.Tensor, name: str = "S"):
+        self._lp = log_prob_per_gene.reshape(-1, 1)
+        self._name = name
+        super().__init__(batch_shape=self._lp.shape, event_shape=torch.Size(), validate_args=False)
+
+    def expand(self, batch_shape, _instance=None):
+        if tuple(batch_shape) != tuple(self.batch_shape):
+            raise ValueError(f"FusedCountLikelihood cannot be expanded to {tuple(batch_shape)}")
+        return self
+
+    def log_prob(self, value):
+        return self._lp
+
+    def sample(self, sample_shape=torch.Size()):
+        raise NotImplementedError(
+            f"site '{self._name}' is an observed-count likelihood; sampling counts from the fused site is not "
+            "supported (condition it on data as the fit drivers do)"
+        )
+
+    def __call__(self, *a, **k):
+        return self.sample(*a, **k)
