@@ -114,6 +114,11 @@ typedef struct vcb_problem {
   float* d_phi;       /* [Nc] total derivative (includes the path through omega(phi)) */
   float* d_cf;        /* [Nc]     */
   float* d_omega;     /* [Nc] partial w.r.t. the per-cell angular speed (informational) */
+
+  /* optional caller-owned cudaEvent_t handles recorded on `stream` right before / after the streaming kernel
+   * (the dominant launch), so that a benchmark can time it without a profiler; NULL = not recorded */
+  void* ev_stream_begin;
+  void* ev_stream_end;
 } vcb_problem_t;
 
 int vcb_version(void);

@@ -26,8 +26,8 @@ def test_library_exports_every_declared_symbol():
 def test_problem_struct_matches_header_layout():
     from velocycle_b200 import _lib
 
-    # 3 int64 + 6 int32/uint32 + 12 pointers + 2*4 spectrum pointers + 11 output pointers
-    assert C.sizeof(_lib.VcbProblem) == 3 * 8 + 6 * 4 + 12 * 8 + 8 * 8 + 11 * 8
+    # 3 int64 + 6 int32/uint32 + 12 pointers + 2*4 spectrum pointers + 11 output pointers + 2 event handles
+    assert C.sizeof(_lib.VcbProblem) == 3 * 8 + 6 * 4 + 12 * 8 + 8 * 8 + 11 * 8 + 2 * 8
     assert C.sizeof(_lib.VcbSpectrum) == 32
 
 

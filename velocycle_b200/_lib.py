@@ -37,6 +37,7 @@ class VcbProblem(C.Structure):
         ("d_nu", C.c_void_p), ("d_dnu", C.c_void_p), ("d_shape_inv", C.c_void_p),
         ("d_logbeta", C.c_void_p), ("d_gamma", C.c_void_p), ("d_nu_omega", C.c_void_p),
         ("d_phi", C.c_void_p), ("d_cf", C.c_void_p), ("d_omega", C.c_void_p),
+        ("ev_stream_begin", C.c_void_p), ("ev_stream_end", C.c_void_p),
     ]
 
 

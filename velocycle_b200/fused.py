@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import VcbProblem, VcbSpectrum, VCB_FLAG_GRAD, VCB_FLAG_LGAMMA_INLINE
+from .sharding import allreduce_flat_
 
 __all__ = ["CountSpectrum", "PackedCounts", "fused_elbo_grad", "FusedCycleNB", "fused_cycle_nb"]
 
@@ -201,8 +202,7 @@ def fused_elbo_grad(
     p.nu, p.dnu, p.shape_inv = nu.data_ptr(), _ptr(dnu), shape_inv.data_ptr()
     out: Dict[str, torch.Tensor] = {}
     f32 = dict(dtype=torch.float32, device=dev)
-    out["lp_S"] = torch.empty(Ng, **f32)
-    p.lp_S = out["lp_S"].data_ptr()
+    Nx = Kw = 0
     if velocity:
         if counts.U is None:
             raise _lib.VcbError("velocity model needs unspliced counts")
@@ -217,34 +217,42 @@ def fused_elbo_grad(
         p.U = counts.U.data_ptr()
         p.cond_id = _ptr(counts.cond_id)
         p.logbeta, p.gamma, p.nu_omega = logbeta.data_ptr(), gamma.data_ptr(), nu_omega.data_ptr()
-        out["lp_U"] = torch.empty(Ng, **f32)
-        p.lp_U = out["lp_U"].data_ptr()
     else:
         p.Hw, p.Nx = 0, 0
+    # every gene-level / global output lives in ONE flat buffer: under cell sharding it is what the single
+    # all-reduce of the step moves (sharding.py)
+    sizes = [("lp_S", Ng), ("lp_U", Ng if velocity else 0)]
+    if grad:
+        sizes += [("d_shape_inv", Ng), ("d_logbeta", Ng if velocity else 0), ("d_gamma", Ng if velocity else 0),
+                  ("d_nu", Ng * K), ("d_dnu", Nb * Ng), ("d_nu_omega", Nx * Kw if velocity else 0)]
+    flat = torch.empty(sum(n for _, n in sizes), **f32)
+    off = 0
+    for name, n in sizes:
+        if n:
+            out[name] = flat[off: off + n]
+            setattr(p, name, out[name].data_ptr())
+        off += n
+    out["gene_flat"] = flat
+    if grad:
+        out["d_nu"] = out["d_nu"].view(Ng, K)
+        if Nb > 0:
+            out["d_dnu"] = out["d_dnu"].view(Nb, Ng)
+        if velocity:
+            out["d_nu_omega"] = out["d_nu_omega"].view(Nx, Kw)
+        out["d_phi"] = torch.empty(Nc, **f32)
+        out["d_cf"] = torch.empty(Nc, **f32)
+        p.d_phi, p.d_cf = out["d_phi"].data_ptr(), out["d_cf"].data_ptr()
+        if velocity and want_d_omega:
+            out["d_omega"] = torch.empty(Nc, **f32)
+            p.d_omega = out["d_omega"].data_ptr()
     if not inline_lgamma:
         counts.build_spectra()
         p.spec_S = counts.spec_S.as_struct()
         if velocity:
             p.spec_U = counts.spec_U.as_struct()
-    if grad:
-        out["d_nu"] = torch.empty(Ng, K, **f32)
-        out["d_shape_inv"] = torch.empty(Ng, **f32)
-        out["d_phi"] = torch.empty(Nc, **f32)
-        out["d_cf"] = torch.empty(Nc, **f32)
-        p.d_nu, p.d_shape_inv = out["d_nu"].data_ptr(), out["d_shape_inv"].data_ptr()
-        p.d_phi, p.d_cf = out["d_phi"].data_ptr(), out["d_cf"].data_ptr()
-        if Nb > 0:
-            out["d_dnu"] = torch.empty(Nb, Ng, **f32)
-            p.d_dnu = out["d_dnu"].data_ptr()
-        if velocity:
-            out["d_logbeta"] = torch.empty(Ng, **f32)
-            out["d_gamma"] = torch.empty(Ng, **f32)
-            out["d_nu_omega"] = torch.empty(Nx, Kw, **f32)
-            p.d_logbeta, p.d_gamma = out["d_logbeta"].data_ptr(), out["d_gamma"].data_ptr()
-            p.d_nu_omega = out["d_nu_omega"].data_ptr()
-            if want_d_omega:
-                out["d_omega"] = torch.empty(Nc, **f32)
-                p.d_omega = out["d_omega"].data_ptr()
+    ev = getattr(counts, "profile_events", None)  # (begin, end) raw cudaEvent_t handles, set by bench.py
+    if ev is not None:
+        p.ev_stream_begin, p.ev_stream_end = ev
     ws_bytes = lib.vcb_workspace_bytes(C.byref(p))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     fn = lib.vcb_velocity_fwd_bwd if velocity else lib.vcb_phase_fwd_bwd
@@ -270,6 +278,7 @@ class FusedCycleNB(torch.autograd.Function):
         grad = any(needs)
         out = fused_elbo_grad(counts, phi, cf, nu, dnu, shape_inv, logbeta, gamma, nu_omega,
                               grad=grad, inline_lgamma=inline_lgamma)
+        allreduce_flat_(out["gene_flat"], getattr(counts, "shard", None))  # the step's single exchange
         ctx.velocity = velocity
         ctx.grad_computed = grad
         ctx.shapes = [None if t is None else t.shape for t in (phi, cf, nu, dnu, shape_inv, logbeta, gamma, nu_omega)]

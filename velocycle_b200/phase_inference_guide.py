@@ -14,6 +14,17 @@ from .ppl import backend
 __all__ = ["phase_latent_variable_guide"]
 
 
+def _phixy_guide_dist(dist, mp, locs, scale):
+    """Normal(phixy_locs, 1) over the cells of this rank.  Under cell sharding the noise is the rank's slice of
+    the global draw, so that all ranks consume the RNG stream like the single-GPU run (sharding.ShardedNormal)."""
+    shard = getattr(mp, "shard", None)
+    if shard is not None and shard.world > 1:
+        from .sharding import ShardedNormal
+
+        return ShardedNormal(locs, scale, shard, event_dims=1)
+    return dist.Normal(locs, scale).to_event(1)
+
+
 def phase_latent_variable_guide(mp):
     pyro, dist, _, _, _ = backend.get()
     dev = mp.device
@@ -41,4 +52,4 @@ def phase_latent_variable_guide(mp):
             with batches:
                 pyro.sample("Δν", dist.Delta(dnu_locs))
     with cells:
-        pyro.sample("ϕxy", dist.Normal(phixy_locs, torch.tensor(1.0, device=dev)).to_event(1))
+        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, torch.tensor(1.0, device=dev)))

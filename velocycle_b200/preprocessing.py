@@ -61,7 +61,7 @@ def _pack(S_cells_by_genes: torch.Tensor, device) -> torch.Tensor:
 def make_phase_metaparams(
     S, U, mu_nu, sd_nu, phixy_prior, batch_id=None, Nb=1, count_factor=None, n_harmonics=None,
     with_delta_nu=True, μΔν=0.0, σΔν=0.5, gamma_alpha=1.0, gamma_beta=2.0, device="cuda",
-    cycle_prior=None, phase_prior=None, spectrum=True,
+    cycle_prior=None, phase_prior=None, spectrum=True, shard=None,
 ):
     """Tensor-level builder.  S, U: (Nc, Ng) counts (any dtype/device); mu_nu, sd_nu: (Ng, K); phixy_prior (Nc,2)."""
     device = torch.device(device)
@@ -91,8 +91,10 @@ def make_phase_metaparams(
         σgc=f(0.5), with_delta_nu=with_delta_nu, μΔν=f(μΔν), σΔν=f(σΔν),
         count_factor=f(count_factor).reshape(1, 1, 1, Nc),
         S=Sp[:, :Ng].T, U=None if Up is None else Up[:, :Ng].T,  # logical (Ng,Nc) views of the packed buffers
-        packed_counts=counts,
+        packed_counts=counts, shard=shard,
     )
+    if counts is not None:
+        counts.shard = shard
     return _container(d)
 
 
@@ -101,7 +103,7 @@ def make_velocity_metaparams(
     count_factor=None, n_harmonics=None, ω_n_harmonics=None, with_delta_nu=True, model_type="lrmn",
     μγ=0.0, σγ=0.5, μβ=2.0, σβ=3.0, μΔν=0.0, σΔν=0.1, gamma_alpha=1.0, gamma_beta=2.0,
     rho_mean=4.0, rho_std=1.0, rho_scale=1.0, rho_rank=5, device="cuda",
-    cycle_prior=None, phase_prior=None, speed_prior=None,
+    cycle_prior=None, phase_prior=None, speed_prior=None, shard=None,
 ):
     """Tensor-level builder.  mu_nu_omega, sd_nu_omega: (Nx, Kw)."""
     device = torch.device(device)
@@ -137,8 +139,10 @@ def make_velocity_metaparams(
         kwargsζ=dict(num_harmonics=H), kwargsζ_dϕ=dict(num_harmonics=H), kwargsζω=dict(num_harmonics=Hw),
         σₛgc=f(0.1), σᵤgc=f(0.1), S=Sp[:, :Ng].T, U=Up[:, :Ng].T, device=device, model_type=model_type,
         rho_mean=f(rho_mean), rho_std=f(rho_std), rho_scale=f(rho_scale), rho_rank=torch.tensor(int(rho_rank)),
-        packed_counts=counts,
+        packed_counts=counts, shard=shard,
     )
+    if counts is not None:
+        counts.shard = shard
     return _container(d)
 
 

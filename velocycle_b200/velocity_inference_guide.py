@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import torch
 
+from .phase_inference_guide import _phixy_guide_dist
 from .ppl import backend
 
 __all__ = ["velocity_latent_variable_guide", "velocity_latent_variable_guide_LRMN"]
@@ -63,7 +64,7 @@ def velocity_latent_variable_guide(mp):
     with harmonics, conditions:
         pyro.sample("νω", dist.Normal(nuw_locs, nuw_scales))
     with cells:
-        pyro.sample("ϕxy", dist.Normal(phixy_locs, torch.tensor(1.0).to(dev)).to_event(1))
+        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, torch.tensor(1.0).to(dev)))
 
 
 def velocity_latent_variable_guide_LRMN(mp):
@@ -130,4 +131,4 @@ def velocity_latent_variable_guide_LRMN(mp):
             tail = tail.reshape((mp.Nx, mp.Nhω))
         pyro.sample("νω", dist.Delta(tail.unsqueeze(-1).unsqueeze(-1)))
     with cells:
-        pyro.sample("ϕxy", dist.Normal(phixy_locs, 1.0).to_event(1))
+        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, 1.0))
