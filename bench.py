@@ -6,7 +6,8 @@
 
 A "step" is one full SVI step of the velocity model (guide draw -> fused ELBO + every gradient over the
 spliced and unspliced count matrices -> gene-gradient all-reduce when N > 1 -> ClippedAdam) through the public
-API ``SVI(model, guide, optim, Trace_ELBO()).step(mp)`` on synthetic counts.  Workload per GPU (weak scaling):
+API ``GraphedSVI(model, guide, optim_args, mp).step()`` (the drop-in model/guide functions traced once into a
+CUDA graph; ``--eager`` times ``ppl.infer.SVI.step`` instead) on synthetic counts, loss read back every step.  Workload per GPU (weak scaling):
 1,000,000 cells x 2,000 genes, 3 gene harmonics, 1 angular-speed harmonic -- the single-GPU target shape of
 BASELINE.json's north_star; 16 GB of fp32 counts per GPU, far beyond the 126 MB L2, so no flush is needed.
 
@@ -54,6 +55,7 @@ def parse():
     ap.add_argument("--conditions", type=int, default=1)
     ap.add_argument("--model-type", default="lrmn", choices=["lrmn", "normal"])
     ap.add_argument("--cpu-sample-cells", type=int, default=4000)
+    ap.add_argument("--eager", action="store_true", help="time the eager ppl.infer.SVI.step instead of GraphedSVI")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -261,7 +263,17 @@ def run_ours(a):
 
     pyro.clear_param_store()
     pyro.set_rng_seed(0)  # same seed on every rank: replicated draws agree, per-cell noise is sliced (ShardedNormal)
-    svi = SVI(mp.model_fn, mp.guide_fn, ClippedAdam({"lr": 0.03, "lrd": 0.9996, "betas": (0.8, 0.99)}), Trace_ELBO())
+    opt_args = {"lr": 0.03, "lrd": 0.9996, "betas": (0.8, 0.99)}
+    if a.eager:
+        eager = SVI(mp.model_fn, mp.guide_fn, ClippedAdam(opt_args), Trace_ELBO())
+        svi_step = lambda: eager.step(mp)
+        launches_per_step, api = 4, "ppl.infer.SVI.step (eager)"
+    else:
+        from velocycle_b200.svi import GraphedSVI
+
+        graphed = GraphedSVI(mp.model_fn, mp.guide_fn, opt_args, mp)
+        svi_step = lambda: graphed.step()
+        launches_per_step, api = 6, "svi.GraphedSVI.step (CUDA graph)"
 
     def barrier():
         if world > 1:
@@ -269,14 +281,14 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     for _ in range(a.warmup):
-        svi.step(mp)
+        svi_step()
     barrier()
     sampler, path = start_clock_sampler(local_rank) if rank == 0 else (None, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
     e0.record()
     for _ in range(a.steps):
-        svi.step(mp)  # returns the loss as a Python float: one D2H read + sync per step, as in the reference
+        svi_step()  # returns the loss as a Python float: one D2H read + sync per step, as in the reference
         kern_ms.append(ev.elapsed_ms())
     e1.record()
     barrier()
@@ -325,7 +337,7 @@ def run_ours(a):
             def e2e_step():
                 counts.S[:rows].copy_(hS, non_blocking=True)
                 counts.U[:rows].copy_(hU, non_blocking=True)
-                return svi.step(mp)
+                return svi_step()
             e2e_step()
             barrier()
             e0.record()
@@ -368,8 +380,10 @@ def run_ours(a):
                        "zero_fraction_S": zero_S, "zero_fraction_U": zero_U, "parallelism": f"cell-shard x{world}"},
             "svi_steps_per_sec": 1e3 / ms_per_step,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": a.steps * 4,
-            "gpu_launches_note": "per step: vcb_cell_tables, vcb_stream_kernel, vcb_cell_epilogue, vcb_gene_epilogue",
+            "gpu_launches": a.steps * launches_per_step,
+            "gpu_launches_note": "our kernels per step: vcb_cell_tables, vcb_stream_kernel, vcb_cell_epilogue, "
+                                 "vcb_gene_epilogue (+ vcb_adam_tick, vcb_clipped_adam under GraphedSVI)",
+            "api": api,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 
+from ._const import const
 from .ppl import backend
 
 __all__ = ["phase_latent_variable_guide"]
@@ -52,4 +53,4 @@ def phase_latent_variable_guide(mp):
             with batches:
                 pyro.sample("Δν", dist.Delta(dnu_locs))
     with cells:
-        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, torch.tensor(1.0, device=dev)))
+        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, const(1.0, dev)))

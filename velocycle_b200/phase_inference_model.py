@@ -14,6 +14,7 @@ import logging
 import numpy as np
 import torch
 
+from ._const import const
 from .fused import fused_cycle_nb
 from .likelihood import FusedCountLikelihood, packed_counts_for
 from .phase_inference_guide import phase_latent_variable_guide
@@ -37,9 +38,9 @@ def phase_latent_variable_model(mp):
         nu = pyro.sample("ν", dist.Normal(mp.μνg.to(dev), mp.σνg.to(dev)).to_event(1))
         if mp.with_delta_nu:
             with batches:
-                dnu = pyro.sample("Δν", dist.Normal(0, mp.σΔν.to(dev)))
+                dnu = pyro.sample("Δν", dist.Normal(const(0.0, dev), mp.σΔν.to(dev)))
     with cells:
-        phixy = pyro.sample("ϕxy", dist.Normal(mp.φxy_prior.to(dev), torch.tensor(1.0, device=dev)).to_event(1))
+        phixy = pyro.sample("ϕxy", dist.Normal(mp.φxy_prior.to(dev), const(1.0, dev)).to_event(1))
     phi = pack_direction(phixy)
     pyro.deterministic("ϕ", phi)
     pyro.deterministic("ζ", torch_fourier_basis(phi.squeeze(), num_harmonics=mp.num_harmonics_S, der=0))

@@ -1,0 +1,164 @@
+"""GraphedSVI: the whole SVI step as one CUDA graph.
+
+``pyro.infer.SVI.step`` (driven by the reference at ``phase_inference_model.py:168-169`` /
+``velocity_inference_model.py:118-120``) costs, besides the likelihood, a few hundred tiny launches and about a
+dozen host syncs per step: guide sampling, prior log-probs, ``.item()`` per site, autograd bookkeeping and one
+``ClippedAdam`` object per parameter tensor.  At 100k cells x 2k genes that host-bound tail is ten times longer
+than the fused likelihood kernel.  ``GraphedSVI`` keeps the model / guide functions and their semantics but
+
+* moves every (unconstrained) parameter into ONE flat fp32 buffer (gradients, Adam moments likewise),
+* traces guide and model once through the effect handlers while a CUDA graph is being captured -- so the graph
+  holds exactly the kernels of one Trace_ELBO step: guide draws (graph-safe Philox RNG), the fused C-ABI launch
+  sequence, the NCCL all-reduce under cell sharding, the backward, and
+* ends with the fused multi-tensor ``vcb_clipped_adam`` kernel (device-side step counter, so replays advance it).
+
+``step()`` replays the graph and reads back the loss (one 4-byte D2H copy).  Distribution argument validation is
+switched off inside the graph (it would need host syncs); run a few eager ``ppl.infer.SVI`` steps first if you
+want Pyro-style validation of a new model.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import _lib
+from .ppl import backend
+
+__all__ = ["GraphedSVI"]
+
+
+class GraphedSVI:
+    def __init__(self, model: Callable, guide: Callable, optim_args: Dict, mp, use_graph: bool = True,
+                 warmup_iters: int = 3):
+        self.model, self.guide, self.mp = model, guide, mp
+        self.lr0 = float(optim_args.get("lr", 1e-3))
+        self.lrd = float(optim_args.get("lrd", 1.0))
+        self.betas = tuple(optim_args.get("betas", (0.9, 0.999)))
+        self.eps = float(optim_args.get("eps", 1e-8))
+        self.clip = float(optim_args.get("clip_norm", 10.0))
+        if float(optim_args.get("weight_decay", 0.0)) != 0.0:
+            raise NotImplementedError("weight_decay is not supported by the fused ClippedAdam")
+        self.device = torch.device(mp.device)
+        if self.device.type != "cuda":
+            raise _lib.VcbError("GraphedSVI needs a CUDA device: velocycle_b200 has no CPU path")
+        self._lib = _lib.load()
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._use_graph = use_graph
+        self._warmup_iters = warmup_iters
+        self._built = False
+        self.steps_done = 0
+
+    # ------------------------------------------------------------------------------------------------------
+    def _flatten_params(self) -> None:
+        """Create the parameters (one eager guide+model pass) and re-home them into one flat buffer."""
+        pyro, _, poutine, _, _ = backend.get()
+        with torch.no_grad():
+            gt = poutine.trace(self.guide).get_trace(self.mp)
+            poutine.trace(poutine.replay(self.model, trace=gt)).get_trace(self.mp)
+        store = pyro.get_param_store()
+        names = list(store.keys())
+        sizes = [store.get_unconstrained(n).numel() for n in names]
+        total = sum(sizes)
+        dev = self.device
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.loss_buf = torch.zeros((), dtype=torch.float32, device=dev)
+        off = 0
+        self.param_slices = {}
+        for n, sz in zip(names, sizes):
+            old = store.get_unconstrained(n)
+            view = self.flat_param[off: off + sz].view(old.shape)
+            view.copy_(old.detach())
+            view.requires_grad_(True)
+            view.grad = self.flat_grad[off: off + sz].view(old.shape)
+            store.set_unconstrained(n, view, store.get_constraint(n))
+            self.param_slices[n] = (off, sz)
+            off += sz
+
+    def _body(self) -> None:
+        """One Trace_ELBO(num_particles=1) step with every value kept on the device."""
+        _, _, poutine, _, _ = backend.get()
+        self.flat_grad.zero_()
+        guide_trace = poutine.trace(self.guide).get_trace(self.mp)
+        model_trace = poutine.trace(poutine.replay(self.model, trace=guide_trace)).get_trace(self.mp)
+        model_trace.compute_log_prob()
+        guide_trace.compute_log_prob()
+        surrogate = 0.0
+        for site in model_trace.nodes.values():
+            if site["type"] == "sample":
+                surrogate = surrogate + site["log_prob_sum"]
+        for site in guide_trace.nodes.values():
+            if site["type"] == "sample":
+                surrogate = surrogate - site["log_prob_sum"]
+        loss = -surrogate
+        loss.backward()
+        self.loss_buf.copy_(loss.detach())
+        rc = self._lib.vcb_clipped_adam(
+            self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+            self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.step_dev.data_ptr(),
+            self.lr0, self.lrd, self.betas[0], self.betas[1], self.eps, self.clip,
+            torch.cuda.current_stream(self.device).cuda_stream,
+        )
+        _lib.check(rc, "vcb_clipped_adam")
+
+    def _build(self) -> None:
+        from .ppl import primitives
+
+        # creating the parameters runs the guide once; put the RNG streams back so that step 1 sees the draws
+        # a fresh ``SVI.step`` would see
+        rng_cuda, rng_cpu = torch.cuda.get_rng_state(self.device), torch.get_rng_state()
+        self._flatten_params()
+        torch.cuda.set_rng_state(rng_cuda, self.device)
+        torch.set_rng_state(rng_cpu)
+        self._validation_prev = primitives.validation_enabled()
+        if not self._use_graph:
+            self._built = True
+            return
+        primitives.enable_validation(False)
+        prev = torch.distributions.Distribution._validate_args
+        torch.distributions.Distribution.set_default_validate_args(False)
+        try:
+            # warm-up on a side stream (lazy kernel attribute setup, allocator pools), with state restored after
+            snap = (self.flat_param.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone())
+            rng = torch.cuda.get_rng_state(self.device)
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                for _ in range(self._warmup_iters):
+                    self._body()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            torch.cuda.synchronize(self.device)
+            with torch.no_grad():
+                self.flat_param.copy_(snap[0])
+                self.exp_avg.copy_(snap[1])
+                self.exp_avg_sq.copy_(snap[2])
+                self.step_dev.copy_(snap[3])
+            torch.cuda.set_rng_state(rng, self.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._body()
+        finally:
+            torch.distributions.Distribution.set_default_validate_args(prev)
+            primitives.enable_validation(self._validation_prev)
+        self._built = True
+
+    # ------------------------------------------------------------------------------------------------------
+    def step(self, *args, sync: bool = True):
+        """One SVI step.  Returns the ELBO loss as a float (``sync=True``, like ``pyro.infer.SVI.step``) or the
+        device scalar that will hold it (``sync=False``)."""
+        if not self._built:
+            self._build()
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._body()
+        self.steps_done += 1
+        return self.loss_buf.item() if sync else self.loss_buf
+
+    def current_lr(self) -> float:
+        return self.lr0 * self.lrd ** self.steps_done

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import torch
 
+from ._const import const
 from .phase_inference_guide import _phixy_guide_dist
 from .ppl import backend
 
@@ -64,7 +65,7 @@ def velocity_latent_variable_guide(mp):
     with harmonics, conditions:
         pyro.sample("νω", dist.Normal(nuw_locs, nuw_scales))
     with cells:
-        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, torch.tensor(1.0).to(dev)))
+        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, const(1.0, dev)))
 
 
 def velocity_latent_variable_guide_LRMN(mp):
@@ -88,10 +89,10 @@ def velocity_latent_variable_guide_LRMN(mp):
     loc = pyro.param("loc", torch.hstack([mp.μγ.squeeze().detach().clone(), mp.μνω.squeeze().detach().clone().flatten()]))
     cov_factor = pyro.param(
         "cov_factor",
-        torch.clip(
-            torch.normal(torch.zeros((n_joint, rank), device=dev), torch.ones((n_joint, rank), device=dev) * 0.02),
-            min=0, max=None,
-        ).to(dev),
+        # == torch.clip(torch.normal(zeros, ones * 0.02), min=0): that overload draws N(0,1) and scales it; this
+        # spelling consumes the RNG stream identically (the reference re-evaluates the initialiser on every
+        # call) but has no host-side check of ``std``, so it can be captured into a CUDA graph
+        torch.clip(torch.empty((n_joint, rank), device=dev).normal_() * 0.02, min=0, max=None),
         constraint=positive,
     )
     cov_diag = pyro.param(
@@ -99,7 +100,14 @@ def velocity_latent_variable_guide_LRMN(mp):
         (torch.hstack([mp.σγ.squeeze().detach().clone(), mp.σνω.squeeze().detach().clone().flatten()]) ** 2).to(dev),
         constraint=positive,
     )
-    joint = dist.LowRankMultivariateNormal(loc=loc, cov_factor=cov_factor, cov_diag=cov_diag).rsample()
+    # = LowRankMultivariateNormal(loc, cov_factor, cov_diag).rsample(): same two standard-normal draws in the
+    # same order (eps_W then eps_D), without the constructor's Cholesky of the capacitance matrix, which the
+    # reference pays every step although only rsample is used (and which would force a host sync on CUDA)
+    from torch.distributions.utils import _standard_normal
+
+    eps_W = _standard_normal(cov_factor.shape[-1:], dtype=loc.dtype, device=loc.device)
+    eps_D = _standard_normal(loc.shape, dtype=loc.dtype, device=loc.device)
+    joint = loc + torch.matmul(cov_factor, eps_W.unsqueeze(-1)).squeeze(-1) + cov_diag.sqrt() * eps_D
     rho_real_loc = pyro.param("rho_real_loc", torch.ones(Ng, device=dev) * mp.rho_mean)
     nb = mp.noisemodel == "NegativeBinomial"
     if nb:
@@ -131,4 +139,4 @@ def velocity_latent_variable_guide_LRMN(mp):
             tail = tail.reshape((mp.Nx, mp.Nhω))
         pyro.sample("νω", dist.Delta(tail.unsqueeze(-1).unsqueeze(-1)))
     with cells:
-        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, 1.0))
+        pyro.sample("ϕxy", _phixy_guide_dist(dist, mp, phixy_locs, const(1.0, dev)))

@@ -15,6 +15,7 @@ import logging
 import numpy as np
 import torch
 
+from ._const import const
 from .fused import fused_cycle_nb
 from .likelihood import FusedCountLikelihood, packed_counts_for
 from .ppl import backend
@@ -49,9 +50,9 @@ def _velocity_model(mp, lrmn: bool):
         nu = pyro.sample("ν", dist.Normal(mp.μνg.to(dev), mp.σνg.to(dev)).to_event(1))
         if mp.with_delta_nu:
             with batches:
-                dnu = pyro.sample("Δν", dist.Normal(torch.tensor(0.0, device=dev), torch.tensor(0.01, device=dev)))
+                dnu = pyro.sample("Δν", dist.Normal(const(0.0, dev), const(0.01, dev)))
     with cells:
-        phixy = pyro.sample("ϕxy", dist.Normal(mp.φxy_prior.to(dev), torch.tensor(1.0, device=dev)).to_event(1))
+        phixy = pyro.sample("ϕxy", dist.Normal(mp.φxy_prior.to(dev), const(1.0, dev)).to_event(1))
     phi = pack_direction(phixy)
     pyro.deterministic("ϕ", phi)
     pyro.deterministic("ζ", torch_basis(phi, der=0, kind=mp.basis_kind, **mp.kwargsζ))
