@@ -483,10 +483,17 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
                     dnu_acc,  p->Nc,                 p->Ng, p->ld,  pl.n_split,
                     p->Nb, getenv("VCB_DEBUG_SKIP_COMPUTE") != nullptr ? 1 : 0};
     dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.n_split);
-    if (p->ev_stream_begin) cudaEventRecord((cudaEvent_t)p->ev_stream_begin, st);
+    // timing events: inside a stream capture they must become event-record NODES (external flag)
+    unsigned ev_flags = cudaEventRecordDefault;
+    if (p->ev_stream_begin || p->ev_stream_end) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+        ev_flags = cudaEventRecordExternal;
+    }
+    if (p->ev_stream_begin) cudaEventRecordWithFlags((cudaEvent_t)p->ev_stream_begin, st, ev_flags);
     e = launch_stream(p->H, velo, grad, lgi, pl.np, sp, grid, pl.nthr, pl.smem, st);
     if (e != cudaSuccess) return (int)e;
-    if (p->ev_stream_end) cudaEventRecord((cudaEvent_t)p->ev_stream_end, st);
+    if (p->ev_stream_end) cudaEventRecordWithFlags((cudaEvent_t)p->ev_stream_end, st, ev_flags);
   }
   if (grad && p->Nc > 0) {
     CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,

@@ -30,7 +30,7 @@
 namespace vcb {
 
 constexpr int kCellsPerStage = 4;  // R (power of two <= 32: the warp reduce-scatter splits lanes by cell)
-constexpr int kStages = 4;         // ring depth
+constexpr int kStages = 6;         // ring depth (6 x 32 KB of counts in flight per SM at 1024-gene tiles)
 // A thread owns NP packed gene pairs.  NP = 1: up to 512 threads/CTA at <=128 registers (16 warps/SM);
 // NP = 2: up to 256 threads/CTA at <=255 registers (8 warps/SM, half the per-cell table traffic per gene).
 __host__ __device__ constexpr int max_threads(int NP) { return NP == 1 ? 512 : 256; }
