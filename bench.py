@@ -233,8 +233,11 @@ def run_ours(a):
     dev = torch.device("cuda", local_rank)
     if rank == 0:
         ge.build()
+    log = (lambda *m: print(f"[bench rank {rank}]", *m, file=sys.stderr, flush=True)) if os.environ.get("VCB_BENCH_VERBOSE") else (lambda *m: None)
+    log("built")
     if world > 1:
         dist.barrier()
+    log("first barrier passed")
 
     Nc, Ng = a.cells_per_gpu, a.genes
     shard = ShardInfo(rank, world, rank * Nc, Nc * world) if world > 1 else None
@@ -255,6 +258,7 @@ def run_ours(a):
                                   batch_id=d.batch_id, cond_id=d.cond_id, Nb=a.batches, Nx=a.conditions,
                                   count_factor=d.cf, model_type=a.model_type, device=dev, shard=shard)
     zero_S, zero_U = d.zero_frac_S, d.zero_frac_U
+    log("metaparams ready")
     del d
     torch.cuda.empty_cache()
     counts = mp.packed_counts
@@ -280,10 +284,11 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler, path = start_clock_sampler(local_rank) if rank == 0 else (None, None)
     for _ in range(a.warmup):
         svi_step()
     barrier()
-    sampler, path = start_clock_sampler(local_rank) if rank == 0 else (None, None)
+    log("warm-up done")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
     e0.record()
@@ -387,11 +392,20 @@ def run_ours(a):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # NCCL communicators referenced by a captured CUDA graph do not tear down cleanly
+        # (destroy_process_group blocks); everything is printed, so leave without the teardown
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
+    import faulthandler
+
+    # never hang a GPU box: dump every thread's stack and exit if the run exceeds the watchdog
+    faulthandler.dump_traceback_later(int(os.environ.get("VCB_BENCH_WATCHDOG_S", "900")), exit=True)
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
