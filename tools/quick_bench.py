@@ -26,7 +26,28 @@ def run(Nc, Ng, velocity=True, H=3, iters=5, inline=False, Nb=1, Nx=1):
           f"({nb/ms/1e6/6518.6*100:.1f}% of measured HBM)  zeros S/U={d.zero_frac_S:.2f}/{d.zero_frac_U:.2f} spectrum {t_spec*1e3:.0f} ms "
           f"maxk={counts.spec_S.max_count if counts.spec_S else -1}", flush=True)
 
+def kernels(Nc, Ng, velocity=True, H=3):
+    """Per-kernel device times of one fused step (torch.profiler / CUPTI)."""
+    from torch.profiler import profile, ProfilerActivity
+    d = make_synthetic(Nc, Ng, H=H, Hw=1, seed=0, device="cuda", stats=False)
+    counts = PackedCounts(d.S, d.U if velocity else None, d.Ng, d.batch_id, d.cond_id)
+    gamma = torch.exp(d.loggamma)
+    args = (counts, d.phi, d.cf, d.nu, d.dnu, d.shape_inv) + ((d.logbeta, gamma, d.nu_omega) if velocity else ())
+    for _ in range(2):
+        fused_elbo_grad(*args, grad=True)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            fused_elbo_grad(*args, grad=True)
+        torch.cuda.synchronize()
+    for e in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:8]:
+        print(f"   {e.key[:70]:70s} n={e.count:3d} avg={e.device_time_total / e.count / 1e3:8.3f} ms", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "kernels":
+        kernels(int(sys.argv[2]), int(sys.argv[3]))
+        sys.exit(0)
     print("VCB_PAIRS_PER_THREAD =", os.environ.get("VCB_PAIRS_PER_THREAD"))
     run(100_000, 2000, True)
     run(100_000, 2000, False)

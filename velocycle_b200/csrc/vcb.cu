@@ -17,9 +17,10 @@
 namespace vcb {
 
 // ======================================================================================================
-// Per-cell prologue: Fourier tables.  One thread per cell.
-//   row = pairs {z,z} of [zeta_1..zeta_2H | zeta'_1..zeta'_2H | zeta''_1..zeta''_2H | omega | cf], then batch | pad
-// Column order [sin, cos] per harmonic and sin(fl(n*phi)) follow utils.py:420-435.
+// Per-cell prologue: the operand table of every 8-cell group (layout: vcb_stream.cuh, TabSection).
+// One warp per group: lanes 0..7 evaluate the Fourier basis of their cell (column order [sin, cos] per harmonic
+// and sin(fl(n*phi)) follow utils.py:420-435), then every lane gathers the two operand values each section
+// expects in its MMA B fragment, splits them into TF32 hi/lo and stores one float4 (coalesced 512 B rows).
 // ======================================================================================================
 struct CellParams {
   const float* phi;
@@ -28,55 +29,97 @@ struct CellParams {
   const int32_t* cond_id;
   const float* nu_omega;  // [Nx][Kw] or null
   float* tab;
-  long long Nc;
-  int H, Hw, Nx, tabw;
+  long long Nc, n_groups;
+  int H, Hw, Nx, velo, tabg;
 };
 
-__global__ void vcb_cell_tables_kernel(const CellParams P) {
-  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.Nc) return;
-  const float phi = P.phi[c];
-  float* row = P.tab + c * P.tabw;
-  const int H = P.H;
-  auto put = [&](int pair, float v) {  // every entry twice: a broadcast LDS.128 then yields {z,z} operands
-    row[2 * pair] = v;
-    row[2 * pair + 1] = v;
-  };
-  for (int n = 1; n <= H; ++n) {
-    float s, co;
-    const float fn = (float)n;
-    sincosf(fn * phi, &s, &co);
-    put(2 * n - 2, s);
-    put(2 * n - 1, co);
-    put(2 * H + 2 * n - 2, fn * co);
-    put(2 * H + 2 * n - 1, -fn * s);
-    put(4 * H + 2 * n - 2, -fn * fn * s);
-    put(4 * H + 2 * n - 1, -fn * fn * co);
-  }
-  float omega = 0.f;
-  if (P.nu_omega != nullptr) {
-    const int x = P.cond_id ? P.cond_id[c] : 0;
-    const int Kw = 2 * P.Hw + 1;
-    const float* nw = P.nu_omega + (long long)x * Kw;
-    omega = nw[0];
-    for (int n = 1; n <= P.Hw; ++n) {
+constexpr int kTabWarps = 8;
+constexpr int kTabSlots = 16;  // 8 * ksteps(VCB_MAX_HARMONICS)
+
+__global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const CellParams P) {
+  // per warp and cell: [0] forward eta operand, [1] zeta', [2] omega*zeta'', [3] backward zeta, [4] omega*zeta'
+  __shared__ float sv[kTabWarps][5][kGroupCells][kTabSlots];
+  __shared__ float s_tail[kTabWarps][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long group = (long long)blockIdx.x * kTabWarps + warp;
+  if (group >= P.n_groups) return;
+  const int H = P.H, K = 2 * H + 1, KS = ksteps(H);
+  if (lane < kGroupCells) {
+    const long long c = group * kGroupCells + lane;
+    const bool valid = c < P.Nc;
+    const long long cl = valid ? c : P.Nc - 1;  // padding cells copy the batch of the last cell
+    const float phi = valid ? P.phi[c] : 0.f;
+    float omega = 0.f;
+    if (P.velo && P.nu_omega != nullptr) {
+      const int x = P.cond_id ? P.cond_id[cl] : 0;
+      const int Kw = 2 * P.Hw + 1;
+      const float* nw = P.nu_omega + (long long)x * Kw;
+      omega = nw[0];
+      for (int n = 1; n <= P.Hw; ++n) {
+        float s, co;
+        sincosf((float)n * phi, &s, &co);
+        omega = fmaf(nw[2 * n - 1], s, omega);
+        omega = fmaf(nw[2 * n], co, omega);
+      }
+    }
+    float(*v)[kGroupCells][kTabSlots] = sv[warp];
+    for (int sec = 0; sec < 5; ++sec)
+      for (int k = 0; k < kTabSlots; ++k) v[sec][lane][k] = 0.f;
+    v[0][lane][0] = 1.f;
+    v[3][lane][0] = 1.f;
+    for (int n = 1; n <= H; ++n) {
       float s, co;
-      sincosf((float)n * phi, &s, &co);
-      omega = fmaf(nw[2 * n - 1], s, omega);
-      omega = fmaf(nw[2 * n], co, omega);
+      const float fn = (float)n;
+      sincosf(fn * phi, &s, &co);
+      const int ks = 2 * n - 1, kc = 2 * n;
+      v[0][lane][ks] = s;
+      v[0][lane][kc] = co;
+      v[3][lane][ks] = s;
+      v[3][lane][kc] = co;
+      v[1][lane][ks] = fn * co;
+      v[1][lane][kc] = -fn * s;
+      v[4][lane][ks] = omega * (fn * co);
+      v[4][lane][kc] = omega * (-fn * s);
+      v[2][lane][ks] = omega * (-fn * fn * s);
+      v[2][lane][kc] = omega * (-fn * fn * co);
+    }
+    // spare slot K: the size factor rides the forward contraction (A holds 1 there); a padding cell gets
+    // eta = -inf so that all its terms vanish; backward it collects sum_c w = d/dgamma
+    v[0][lane][K] = valid ? (P.cf ? P.cf[c] : 0.f) : -1e30f;
+    v[4][lane][K] = 1.f;
+    s_tail[warp][lane] = omega;
+    s_tail[warp][8 + lane] = __int_as_float(P.batch_id ? P.batch_id[cl] : 0);
+  }
+  __syncwarp();
+  const int grp = lane >> 2, q = lane & 3;
+  float4* out = reinterpret_cast<float4*>(P.tab + group * P.tabg);
+  auto emit = [&](int sec_out, int ks, float x0, float x1) {
+    uint32_t h0, l0, h1, l1;
+    split_tf32(x0, h0, l0);
+    split_tf32(x1, h1, l1);
+    out[(sec_out * KS + ks) * 32 + lane] =
+        make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+  };
+  const int fc = fwd_cell(grp);
+  for (int ks = 0; ks < KS; ++ks) {
+    // forward B fragments: b0 (k = q, n = grp), b1 (k = q+4, n = grp); column n is cell fwd_cell(n)
+    emit(SEC_F0, ks, sv[warp][0][fc][8 * ks + q], sv[warp][0][fc][8 * ks + q + 4]);
+    emit(SEC_F1, ks, sv[warp][1][fc][8 * ks + q], sv[warp][1][fc][8 * ks + q + 4]);
+    // backward B fragments: b0 (k = cell q, n = slot grp), b1 (k = cell q+4, n = slot grp)
+    emit(SEC_B0, ks, sv[warp][3][q][8 * ks + grp], sv[warp][3][q + 4][8 * ks + grp]);
+    if (P.velo) {
+      emit(SEC_F2, ks, sv[warp][2][fc][8 * ks + q], sv[warp][2][fc][8 * ks + q + 4]);
+      emit(SEC_B1, ks, sv[warp][4][q][8 * ks + grp], sv[warp][4][q + 4][8 * ks + grp]);
     }
   }
-  put(6 * H, omega);
-  put(6 * H + 1, P.cf ? P.cf[c] : 0.f);
-  row[12 * H + 4] = __int_as_float(P.batch_id ? P.batch_id[c] : 0);
-  for (int i = 12 * H + 5; i < P.tabw; ++i) row[i] = 0.f;
+  if (lane < 16) P.tab[group * P.tabg + table_tail(H, P.velo != 0) + lane] = s_tail[warp][lane];
 }
 
 // ======================================================================================================
 // Per-cell epilogue: sum the gene-tile partials, add the omega(phi) path to d/dphi, reduce d/dnu_omega.
 // ======================================================================================================
 struct CellEpiParams {
-  const float* cellpart;  // [n_part][Nc][NQ], n_part = gene tiles x warps per CTA
+  const float* cellpart;  // [n_part][Ncp][NQ], n_part = gene tiles, Ncp = cells padded to whole groups
   const float* phi;
   const int32_t* cond_id;
   const float* nu_omega;
@@ -84,7 +127,7 @@ struct CellEpiParams {
   float* d_cf;
   float* d_omega;
   double* dnw_acc;  // [Nx*Kw], zeroed
-  long long Nc;
+  long long Nc, Ncp;
   int n_part, NQ, Hw, Nx;
 };
 
@@ -99,7 +142,7 @@ __global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
   if (c < P.Nc) {
     float q[3] = {0.f, 0.f, 0.f};
     for (int t = 0; t < P.n_part; ++t)
-      for (int i = 0; i < P.NQ; ++i) q[i] += P.cellpart[((long long)t * P.Nc + c) * P.NQ + i];
+      for (int i = 0; i < P.NQ; ++i) q[i] += P.cellpart[((long long)t * P.Ncp + c) * P.NQ + i];
     float dphi = q[1];
     if (velo) {
       const float phi = P.phi[c];
@@ -316,8 +359,9 @@ __global__ void vcb_clipped_adam_kernel(float* __restrict__ p, const float* __re
 // Host side
 // ======================================================================================================
 struct Plan {
-  int np, nthr, tile_g, n_tiles, n_split, W_max;
-  int tabw, rows, NQ;
+  int np, nthr, tile_g, n_tiles, n_split, n_ring;
+  int tabg, rows, NQ;
+  long long n_groups, Ncp;
   size_t off_tab, off_genepart, off_cellpart, off_dnuacc, off_dnwacc, total;
   int smem;
 };
@@ -337,8 +381,8 @@ static int sm_count() {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static int pairs_per_thread() {
-  // NP = 1: 512 threads x 2 genes (16 warps/SM, <=128 regs); NP = 2: 256 threads x 4 genes (8 warps/SM, <=255 regs)
+static int pairs_per_warp() {
+  // NPAIR = 1: 512 threads, a warp owns 32 genes (<=128 regs); NPAIR = 2: 256 threads, 64 genes per warp (<=255 regs)
   static int np = 0;
   if (np == 0) {
     const char* e = getenv("VCB_PAIRS_PER_THREAD");
@@ -347,16 +391,17 @@ static int pairs_per_thread() {
   return np;
 }
 
+constexpr int kSmemBudget = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
+
 static Plan make_plan(const vcb_problem_t* p, bool velo) {
   Plan pl{};
-  const bool grad = (p->flags & VCB_FLAG_GRAD) != 0;
-  pl.np = pairs_per_thread();
-  const int gpt = 2 * pl.np;
+  pl.np = pairs_per_warp();
+  const int gpw = 32 * pl.np;  // genes per warp
   const int tmax = max_threads(pl.np);
   // threads per CTA: the widest tile that wastes the fewest lanes
   double best = -1.0;
   for (int t = tmax; t >= 32; t >>= 1) {
-    const long long tg = (long long)gpt * t;
+    const long long tg = (long long)gpw * (t / 32);
     const long long nt = (p->ld + tg - 1) / tg;
     const double eff = (double)p->ld / (double)(nt * tg);
     if (eff > best + 0.02) {
@@ -364,27 +409,34 @@ static Plan make_plan(const vcb_problem_t* p, bool velo) {
       pl.nthr = t;
     }
   }
-  pl.tile_g = gpt * pl.nthr;
+  pl.tile_g = gpw * (pl.nthr / 32);
   pl.n_tiles = (int)((p->ld + pl.tile_g - 1) / pl.tile_g);
   if (pl.n_tiles < 1) pl.n_tiles = 1;
-  pl.W_max = (int)(p->ld < pl.tile_g ? p->ld : pl.tile_g);
+  pl.n_groups = (p->Nc + kGroupCells - 1) / kGroupCells;
+  pl.Ncp = pl.n_groups * kGroupCells;
   const int ctas_per_sm = tmax / pl.nthr;
   long long ns = ((long long)sm_count() * ctas_per_sm) / pl.n_tiles;
-  const long long max_split = (p->Nc + kCellsPerStage - 1) / kCellsPerStage;
-  if (ns > max_split) ns = max_split;
+  if (ns > pl.n_groups) ns = pl.n_groups;
   if (ns < 1) ns = 1;
   pl.n_split = (int)ns;
-  pl.tabw = table_width(p->H);
+  pl.tabg = table_group_floats(p->H, velo);
   pl.rows = gene_rows(p->H);
   pl.NQ = velo ? 3 : 2;
-  pl.smem = stream_smem_layout(p->H, velo, grad, pl.nthr, pl.W_max).total;
+  // ring depth: as deep as the CTA's share of shared memory allows
+  pl.n_ring = 2;
+  for (int r = kMaxStages; r >= 2; --r)
+    if (stream_smem_layout(p->H, velo, pl.nthr / 32, pl.np, r).total <= kSmemBudget / ctas_per_sm - 1024) {
+      pl.n_ring = r;
+      break;
+    }
+  pl.smem = stream_smem_layout(p->H, velo, pl.nthr / 32, pl.np, pl.n_ring).total;
   size_t off = 0;
   pl.off_tab = off;
-  off = align_up(off + (size_t)p->Nc * pl.tabw * 4, 256);
+  off = align_up(off + (size_t)pl.n_groups * pl.tabg * 4, 256);
   pl.off_genepart = off;
   off = align_up(off + (size_t)pl.n_split * pl.rows * p->ld * 4, 256);
   pl.off_cellpart = off;
-  off = align_up(off + (size_t)pl.n_tiles * (pl.nthr / 32) * pl.NQ * p->Nc * 4, 256);
+  off = align_up(off + (size_t)pl.n_tiles * pl.NQ * pl.Ncp * 4, 256);
   pl.off_dnuacc = off;
   off = align_up(off + (size_t)(p->Nb > 0 ? p->Nb : 0) * p->Ng * 4, 256);
   pl.off_dnwacc = off;
@@ -471,17 +523,16 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
   }
   if (p->Nc > 0) {
     CellParams cp{p->phi, p->cf, p->Nb > 0 ? p->batch_id : nullptr, p->cond_id, velo ? p->nu_omega : nullptr,
-                  tab,    p->Nc, p->H, p->Hw, p->Nx, pl.tabw};
-    const int bs = 256;
-    vcb_cell_tables_kernel<<<(unsigned)((p->Nc + bs - 1) / bs), bs, 0, st>>>(cp);
+                  tab,    p->Nc, pl.n_groups, p->H, p->Hw, p->Nx, velo ? 1 : 0, pl.tabg};
+    vcb_cell_tables_kernel<<<(unsigned)((pl.n_groups + kTabWarps - 1) / kTabWarps), kTabWarps * 32, 0, st>>>(cp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   {
     StreamParams sp{p->S,     velo ? p->U : nullptr, tab,   p->nu,  p->Nb > 0 ? p->dnu : nullptr,
                     p->shape_inv, p->logbeta,        p->gamma, genepart, cellpart,
-                    dnu_acc,  p->Nc,                 p->Ng, p->ld,  pl.n_split,
-                    p->Nb, getenv("VCB_DEBUG_SKIP_COMPUTE") != nullptr ? 1 : 0};
+                    dnu_acc,  p->Nc,                 p->Ng, p->ld,  pl.Ncp, pl.n_split,
+                    p->Nb, pl.n_ring, getenv("VCB_DEBUG_SKIP_COMPUTE") != nullptr ? 1 : 0};
     dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.n_split);
     // timing events: inside a stream capture they must become event-record NODES (external flag)
     unsigned ev_flags = cudaEventRecordDefault;
@@ -497,7 +548,7 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
   }
   if (grad && p->Nc > 0) {
     CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
-                     dnw_acc,  p->Nc,  pl.n_tiles * (pl.nthr / 32), pl.NQ, p->Hw, velo ? p->Nx : 0};
+                     dnw_acc,  p->Nc,  pl.Ncp, pl.n_tiles, pl.NQ, p->Hw, velo ? p->Nx : 0};
     const int bs = 256;
     const size_t sm = velo ? (size_t)p->Nx * (2 * p->Hw + 1) * 8 : 0;
     vcb_cell_epilogue_kernel<<<(unsigned)((p->Nc + bs - 1) / bs), bs, sm, st>>>(ce);

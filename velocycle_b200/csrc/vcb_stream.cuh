@@ -1,80 +1,104 @@
 // The streaming kernel: one pass over the [cells][genes] count tiles of S (and U) that produces the
 // per-gene log-prob partial sums AND every gradient partial sum.
 //
+// Where the arithmetic runs.  Per (cell, gene) the path needs three K-term contractions forward
+// (eta = nu.zeta, d = nu.zeta', nu.zeta'') and two backward (d/dnu += gE zeta + w omega zeta'): 31 of the
+// 61 fp32 operations of the element.  The fp32 pipe, not HBM, bounded the first version of this kernel
+// (DESIGN.md section 4), so those contractions now run on the tensor pipe as warp-level m16n8k8 TF32 MMAs
+// (SASS HMMA.1688.F32.TF32) with the 3xTF32 split (x = hi + lo, drop lo*lo) that keeps fp32-level accuracy;
+// the fp32 pipe keeps the negative-binomial terms, the MUFU pipe the 5 transcendentals.  K = 2H+1 <= 7 fits
+// one 8-wide k-step together with one spare slot that carries the per-cell size factor forward and
+// sum_c w (= d/dgamma) backward.  (tcgen05 is the wrong tool here: its operands live in shared memory, and
+// the backward operand gE is produced in registers by the same threads that consume the forward result.)
+//
 // Mapping (genes are the contiguous axis of the counts, preprocessing.py:193-194):
-//   * a CTA owns a gene tile of 2*NP*blockDim genes and a contiguous range of cells;
-//   * a thread owns NP packed pairs of adjacent genes: their Fourier coefficients, dispersion and
-//     kinetics stay in registers for the whole kernel, as do the per-gene accumulators (no atomics on
-//     the hot path).  All fp32 arithmetic is issued as packed f32x2 (FFMA2/FADD2/FMUL2) over a gene
-//     pair: the fp32 pipe, not HBM, bounds this kernel, so halving issue slots matters;
-//   * cells are streamed through a shared-memory ring filled by the TMA engine with 1-D bulk copies
-//     (cp.async.bulk + mbarrier complete_tx); a stage = kCellsPerStage count rows of S and U plus the
-//     per-cell table rows (Fourier basis, its derivatives, omega, size factor -- each stored twice so a
-//     broadcast LDS.128 yields ready-made {z,z} operands -- and the batch id) built by
-//     vcb_cell_tables_kernel; counts are read with one conflict-free LDS.128 per matrix;
-//   * per-cell sums (d/dphi, d/dcf, d/domega run over genes, i.e. across threads) are reduced inside each
-//     warp once per stage with a transposed butterfly (reduce-scatter over the stage's cells, ~2 shuffles
-//     per value instead of 5) and written as per-warp partials; the cell epilogue kernel adds the warps.
-//     No warp ever waits for another warp: the only cross-warp state is the ring's done[] counters that
-//     tell the producer thread when a slot may be refilled.
+//   * a CTA owns a gene tile of 32*NPAIR*warps genes and a contiguous range of 8-cell groups;
+//   * a warp owns 32*NPAIR genes = 2*NPAIR MMA row tiles; lane (grp = lane/4, q = lane%4) owns 4 adjacent
+//     genes per pair (rows grp and grp+8 of two row tiles) x the cells q and q+4 of the group.  Its nu
+//     fragments (hi/lo), dispersion, kinetics and every per-gene accumulator stay in registers for the whole
+//     kernel (no atomics on the hot path).  The forward accumulator fragment of a row tile IS the backward
+//     A fragment ({c0,c2,c1,c3} -> {a0,a1,a2,a3}) once the forward B columns are permuted (column 2j -> cell j,
+//     2j+1 -> cell j+4), so nothing is transposed or shuffled between the two GEMMs;
+//   * cells stream through a shared-memory ring filled by the TMA engine with 1-D bulk copies (cp.async.bulk
+//     + mbarrier complete_tx); a stage = one 8-cell group: 8 count rows of S and of U (row pitch = tile + 8
+//     floats, which makes the per-lane LDS.128 of 4 genes conflict-free) plus the group's operand table built
+//     by vcb_cell_tables_kernel: the B fragments of every MMA, already split hi/lo and stored in lane order;
+//   * per-cell sums (d/dphi, d/dcf, d/domega run over genes, i.e. over grp lanes and warps) are reduced
+//     once per group with 9 shuffles, parked per warp in shared memory and summed in a fixed order by the
+//     warp that later refills the slot (deterministic, no atomics);
+//   * no CTA-wide barrier and no warp waits for another warp in steady state: full[]/done[] mbarriers only,
+//     refills are work-stolen.
 //
 // Arithmetic per (cell, gene), SURVEY.md Appendix A, in units of mu/r and base-2 logs so that every
 // transcendental is a single MUFU op and the n r log r terms cancel analytically:
 //   y = (etaS - ln r) log2e; u = 2^y = muS/r; s = 1+u; LS = lg2 s; gS = (kS - r u)/s
 //   a = d*omega+gamma; m = relu(a)+1e-5; mb = m/beta; uU = u mb; sU = 1+uU; LU = lg2 sU
-//   w0 = (kU - r uU)/(sU m); gU = w0 m; w = 1[a>0] w0
+//   w0 = (kU - r uU)/(sU m); gU = w0 m; w = 1[a>0] w0      (1/s and 1/(sU m) share one MUFU.RCP)
 //   log-prob pieces: kS (y-LS), LS, kU (y+lg2 mb-LU), LU   (times ln2, plus per-gene terms, in the epilogue)
 #pragma once
 #include "vcb_common.cuh"
 
 namespace vcb {
 
-constexpr int kCellsPerStage = 4;  // R (power of two <= 32: the warp reduce-scatter splits lanes by cell)
-constexpr int kStages = 6;         // ring depth (6 x 32 KB of counts in flight per SM at 1024-gene tiles)
-// A thread owns NP packed gene pairs.  NP = 1: up to 512 threads/CTA at <=128 registers (16 warps/SM);
-// NP = 2: up to 256 threads/CTA at <=255 registers (8 warps/SM, half the per-cell table traffic per gene).
-__host__ __device__ constexpr int max_threads(int NP) { return NP == 1 ? 512 : 256; }
+constexpr int kGroupCells = 8;  // cells per ring stage = the n extent (forward) / k extent (backward) of the MMAs
+constexpr int kMaxStages = 8;   // ring depth is chosen on the host to fill shared memory, up to this
+constexpr int kRowPad = 8;      // count rows sit at a pitch of tile+8 floats in shared memory
+constexpr int kFlushEvery = 8;  // d/dnu MMA accumulators are folded into fp32 registers every so many groups
+constexpr int kSmemHeader = 256;
+
+// A warp owns 32*NPAIR genes.  NPAIR = 1: up to 512 threads/CTA at <= 128 registers; NPAIR = 2: up to 256.
+__host__ __device__ constexpr int max_threads(int NPAIR) { return NPAIR == 1 ? 512 : 256; }
 
 // per-gene partial rows written by the streaming kernel
 enum GeneRow { ROW_AS = 0, ROW_LS = 1, ROW_AU = 2, ROW_LU = 3, ROW_GU = 4, ROW_W = 5, ROW_PSI = 6, ROW_DNU = 7 };
-
-// per-cell table row, in floats: pairs {z,z} for zeta[1..2H], zeta'[1..2H], zeta''[1..2H], omega, cf; then batch id
-__host__ __device__ constexpr int table_width(int H) { return ((12 * H + 5) + 3) / 4 * 4; }
 __host__ __device__ constexpr int gene_rows(int H) { return ROW_DNU + 2 * H + 1; }
+
+// Operand table of one 8-cell group: sections of [k-step][lane][4] floats = {hi b0, hi b1, lo b0, lo b1},
+// then omega[8] and batch id[8].  Slots of a k-step row: 0 -> constant, 1..2H -> harmonics, 2H+1 -> spare.
+enum TabSection { SEC_F0 = 0, SEC_F1 = 1, SEC_B0 = 2, SEC_F2 = 3, SEC_B1 = 4 };
+__host__ __device__ constexpr int ksteps(int H) { return (2 * H + 2 + 7) / 8; }
+__host__ __device__ constexpr int table_sections(bool velo) { return velo ? 5 : 3; }
+__host__ __device__ constexpr int table_tail(int H, bool velo) { return table_sections(velo) * ksteps(H) * 128; }
+__host__ __device__ constexpr int table_group_floats(int H, bool velo) { return table_tail(H, velo) + 16; }
+// forward B column n of a group holds cell fwd_cell(n): the accumulator columns {2q, 2q+1} of a lane are then
+// the cells {q, q+4} that the same lane must supply as backward A columns
+__host__ __device__ constexpr int fwd_cell(int n) { return (n >> 1) + 4 * (n & 1); }
 
 struct StreamParams {
   const float* S;
   const float* U;
-  const float* tab;  // [Nc][TABW]
+  const float* tab;  // [n_groups][table_group_floats]
   const float* nu;
   const float* dnu;
   const float* shape_inv;
   const float* logbeta;
   const float* gamma;
   float* genepart;  // [n_split][rows][ld]
-  float* cellpart;  // [n_tiles * warps_per_cta][Nc][NQ]
+  float* cellpart;  // [n_tiles][Ncp][NQ]
   float* d_dnu;     // [Nb][Ng], zeroed, atomically accumulated at batch boundaries
-  long long Nc, Ng, ld;
+  long long Nc, Ng, ld, Ncp;
   int n_split;
   int Nb;
+  int n_ring;              // ring depth
   int debug_skip_compute;  // profiling aid: stream the tiles but skip the arithmetic
 };
 
 struct StreamSmem {
-  int tab_off, cnt_off, total;  // byte offsets inside dynamic shared memory
+  int part_off, tab_off, cnt_off, total;  // byte offsets inside dynamic shared memory
 };
 
-__host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, bool grad, int nthr, int W) {
+__host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, int nwarps, int npair, int n_ring) {
   StreamSmem L;
-  int off = 128;  // mbarriers
+  const int WT = 32 * npair * nwarps;
+  int off = kSmemHeader;  // mbarriers + the refill cursor
+  L.part_off = off;
+  off += n_ring * nwarps * kGroupCells * (velo ? 3 : 2) * 4;
+  off = (off + 127) / 128 * 128;
   L.tab_off = off;
-  off += kStages * kCellsPerStage * table_width(H) * 4;
+  off += n_ring * table_group_floats(H, velo) * 4;
   off = (off + 127) / 128 * 128;
   L.cnt_off = off;
-  off += kStages * (velo ? 2 : 1) * kCellsPerStage * W * 4;
-  off = (off + 127) / 128 * 128;
-  (void)grad;
-  (void)nthr;
+  off += n_ring * (velo ? 2 : 1) * kGroupCells * (WT + kRowPad) * 4;
   L.total = off;
   return L;
 }
@@ -89,117 +113,206 @@ __device__ __forceinline__ float2 ex2_2(float2 a) { return f2(ex2_approx(a.x), e
 __device__ __forceinline__ float2 lg2_2(float2 a) { return f2(lg2_approx(a.x), lg2_approx(a.y)); }
 __device__ __forceinline__ float2 rcp_2(float2 a) { return f2(rcp_approx(a.x), rcp_approx(a.y)); }
 
-template <int H, bool VELO, bool GRAD, bool LGINLINE, int NP>
-__global__ void __launch_bounds__(max_threads(NP), 1) vcb_stream_kernel(const StreamParams P) {
-  constexpr int GPT = 2 * NP;  // genes per thread
+// ---- TF32 tensor-core helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// x = hi + lo with hi, lo representable in TF32 (lo rounded): the operands of the 3xTF32 scheme
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = tf32_rna(x);
+  lo = tf32_rna(x - __uint_as_float(hi));
+}
+// hot-path split: hi by truncation (one LOP), lo = x - hi exactly (the MMA ignores lo's 13 low mantissa bits)
+__device__ __forceinline__ void split_trunc(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// D(16x8) += A(16x8, row) * B(8x8, col).  Fragments (grp = lane/4, q = lane%4):
+//   a0 (grp, q)  a1 (grp+8, q)  a2 (grp, q+4)  a3 (grp+8, q+4);  b0 (k=q, n=grp)  b1 (k=q+4, n=grp);
+//   c0 (grp, 2q)  c1 (grp, 2q+1)  c2 (grp+8, 2q)  c3 (grp+8, 2q+1)
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// C += (Ahi + Alo)(Bhi + Blo) without the lo*lo term, small terms first
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const float4 b) {
+  mma_tf32(c, alo, __float_as_uint(b.x), __float_as_uint(b.y));
+  mma_tf32(c, ahi, __float_as_uint(b.z), __float_as_uint(b.w));
+  mma_tf32(c, ahi, __float_as_uint(b.x), __float_as_uint(b.y));
+}
+
+template <int H, bool VELO, bool GRAD, bool LGINLINE, int NPAIR>
+__global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const StreamParams P) {
   constexpr int K = 2 * H + 1;
-  constexpr int TABW = table_width(H);
+  constexpr int KS = ksteps(H);
+  constexpr int NT = 2 * NPAIR;  // MMA row tiles per warp
   constexpr int NMAT = VELO ? 2 : 1;
   constexpr int NQ = VELO ? 3 : 2;
-  constexpr int R = kCellsPerStage;
-  constexpr int NS = kStages;
-  constexpr int P_Z1 = 2 * H, P_Z2 = 4 * H, P_OM = 6 * H, P_CF = 6 * H + 1;  // pair indices in a table row
+  constexpr int R = kGroupCells;
+  constexpr int TABG = table_group_floats(H, VELO);
+  constexpr int TAIL = table_tail(H, VELO);
+  constexpr bool NEED_D = GRAD || VELO;
+  constexpr bool NEED_E = GRAD && VELO;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const int grp = lane >> 2, q = lane & 3;
+  const int NS = P.n_ring;
   const int tile = blockIdx.x;
   const int split = blockIdx.y;
-  const long long g_base = (long long)tile * GPT * nthr;
+  const int WT = 32 * NPAIR * nwarps;  // genes per CTA tile
+  const int RS = WT + kRowPad;         // shared-memory pitch of a count row, floats
+  const long long g_base = (long long)tile * WT;
   const long long rem = P.ld - g_base;
-  const int W = (int)(rem < (long long)GPT * nthr ? rem : (long long)GPT * nthr);
-  const StreamSmem L = stream_smem_layout(H, VELO, GRAD, nthr, W);
+  const int W = (int)(rem < (long long)WT ? rem : (long long)WT);  // genes of this tile that exist in a row
+  const StreamSmem L = stream_smem_layout(H, VELO, nwarps, NPAIR, NS);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* full = mbar;  // [NS] each; roles documented where they are initialised
-  uint64_t* done = mbar + NS;
+  uint64_t* full = mbar;  // [kMaxStages] each; roles documented where they are initialised
+  uint64_t* done = mbar + kMaxStages;
+  int* s_next = reinterpret_cast<int*>(mbar + 2 * kMaxStages);
+  float* s_part = reinterpret_cast<float*>(smem_raw + L.part_off);
   float* s_tab = reinterpret_cast<float*>(smem_raw + L.tab_off);
   float* s_cnt = reinterpret_cast<float*>(smem_raw + L.cnt_off);
 
-  // this CTA's cells
-  const long long c0 = (P.Nc * split) / P.n_split;
-  const long long c1 = (P.Nc * (split + 1)) / P.n_split;
-  const int n_cells = (int)(c1 - c0);
-  const int n_stages = (n_cells + R - 1) / R;
+  // this CTA's cell groups
+  const long long n_groups = P.Ncp / R;
+  const long long G0 = (n_groups * split) / P.n_split;
+  const long long G1 = (n_groups * (split + 1)) / P.n_split;
+  const int n_stages = (int)(G1 - G0);
 
-  // ---- per-gene state in registers (pair p holds genes gj+2p, gj+2p+1) ----------------------------
-  const long long gj = g_base + (long long)GPT * tid;
-  const bool has_data = GPT * tid < W;  // this thread's 16 bytes exist in the smem rows
-  float2 nu[K][NP], nr[NP], gam[NP], invb[NP], nu0c[NP];
-  {
-    float nus[K][GPT], rs[GPT], gs[GPT], ibs[GPT], lnr[GPT];
+  // ---- per-gene state in registers ------------------------------------------------------------------
+  // pair p, gene j in 0..3: g = g_base + (warp*NPAIR + p)*32 + 4*grp + j; row tile mt = 2p + (j>>1) holds
+  // gene j in fragment rows grp (j even) and grp+8 (j odd).
+  int gl[NPAIR];       // tile-local index of the lane's first gene of pair p
+  bool gvalid[NPAIR];  // the lane's 16 bytes exist in the shared-memory rows
 #pragma unroll
-    for (int j = 0; j < GPT; ++j) {
-      const long long g = gj + j;
-      if (has_data && g < P.Ng) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) nus[k][j] = P.nu[g * K + k];
-        rs[j] = 1.0f / P.shape_inv[g];
-        gs[j] = VELO ? P.gamma[g] : 1.f;
-        ibs[j] = VELO ? expf(-P.logbeta[g]) : 1.f;
-      } else {  // padding column: eta = -inf makes every contribution exactly zero
-#pragma unroll
-        for (int k = 0; k < K; ++k) nus[k][j] = 0.f;
-        nus[0][j] = -1e30f;
-        rs[j] = 1.f;
-        gs[j] = 1.f;
-        ibs[j] = 1.f;
-      }
-      lnr[j] = logf(rs[j]);
-    }
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) nu[k][p] = f2(nus[k][2 * p], nus[k][2 * p + 1]);
-      nr[p] = f2(-rs[2 * p], -rs[2 * p + 1]);
-      gam[p] = f2(gs[2 * p], gs[2 * p + 1]);
-      invb[p] = f2(ibs[2 * p], ibs[2 * p + 1]);
-      nu0c[p] = f2(nus[0][2 * p] - lnr[2 * p], nus[0][2 * p + 1] - lnr[2 * p + 1]);
-    }
+  for (int p = 0; p < NPAIR; ++p) {
+    gl[p] = (warp * NPAIR + p) * 32 + 4 * grp;
+    gvalid[p] = gl[p] < W;
   }
+  auto gene_of = [&](int mt, int odd) -> long long { return g_base + gl[mt >> 1] + 2 * (mt & 1) + odd; };
+  auto lnr_of = [&](long long g) -> float { return g < P.Ng ? -logf(P.shape_inv[g]) : 0.f; };  // ln r
+  // value of the forward A operand (gene g, slot): [nu0 - ln r (+ dnu[b]), nu_1..nu_2H, 1, 0...]
+  auto a_value = [&](long long g, int slot, int b) -> float {
+    if (g >= P.Ng) return slot == 0 ? -1e30f : 0.f;  // padding gene: eta = -inf makes every contribution zero
+    if (slot == 0) {
+      float v = P.nu[g * K] - lnr_of(g);
+      if (b >= 0) v += P.dnu[(long long)b * P.Ng + g];
+      return v;
+    }
+    if (slot < K) return P.nu[g * K + slot];
+    return slot == K ? 1.f : 0.f;
+  };
+  uint32_t Ahi[NT][KS][4], Alo[NT][KS][4];
+  float2 nr[NT], gam[NT], invb[NT];
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        split_tf32(a_value(gene_of(mt, i & 1), 8 * ks + q + 4 * (i >> 1), -1), Ahi[mt][ks][i], Alo[mt][ks][i]);
+    float rs[2], gs[2], ibs[2];
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const long long g = gene_of(mt, o);
+      const bool ok = g < P.Ng;
+      rs[o] = ok ? 1.0f / P.shape_inv[g] : 1.f;
+      gs[o] = (ok && VELO) ? P.gamma[g] : 1.f;
+      ibs[o] = (ok && VELO) ? expf(-P.logbeta[g]) : 1.f;
+    }
+    nr[mt] = f2(-rs[0], -rs[1]);
+    gam[mt] = f2(gs[0], gs[1]);
+    invb[mt] = f2(ibs[0], ibs[1]);
+  }
+  // slot 0 of the A operand carries the batch offset of the current batch (only the q == 0 lanes hold slot 0)
+  auto set_slot0 = [&](int b) {
+    if (q == 0) {
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) split_tf32(a_value(gene_of(mt, o), 0, b), Ahi[mt][0][o], Alo[mt][0][o]);
+    }
+  };
   int cur_b = -1;
 
   const float2 zero2 = f2s(0.f);
-  float2 accAS[NP], accLS[NP], accAU[NP], accLU[NP], accGU[NP], accW[NP], accPsi[NP];
-  float2 accNu[K][NP];
+  float2 accAS[NT], accLS[NT], accAU[NT], accLU[NT], accGU[NT], accPsi[NT];
+  float accNu[NT][KS][4], accT[NT][KS][4];  // d/dnu fragments: fp32 running sums and the MMA accumulators
 #pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    accAS[p] = accLS[p] = accAU[p] = accLU[p] = accGU[p] = accW[p] = accPsi[p] = zero2;
+  for (int mt = 0; mt < NT; ++mt) {
+    accAS[mt] = accLS[mt] = accAU[mt] = accLU[mt] = accGU[mt] = accPsi[mt] = zero2;
 #pragma unroll
-    for (int k = 0; k < K; ++k) accNu[k][p] = zero2;
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) accNu[mt][ks][i] = accT[mt][ks][i] = 0.f;
   }
+  // Tensor-core accumulation truncates; a long chain of small addends into a large sum would drift, so the
+  // MMA accumulators only ever hold kFlushEvery groups and are folded into fp32 registers with rounding.
+  auto fold_acc = [&]() {
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          accNu[mt][ks][i] += accT[mt][ks][i];
+          accT[mt][ks][i] = 0.f;
+        }
+  };
+  // batch boundary: the constant column of d/dnu (slot 0: lanes q == 0, c0 / c2) is the batch's d/ddnu
+  auto flush_batch = [&]() {
+    fold_acc();
+    if (q == 0 && cur_b >= 0) {
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const long long g = gene_of(mt, o);
+          if (g < P.Ng) atomicAdd(&P.d_dnu[(long long)cur_b * P.Ng + g], accNu[mt][0][2 * o]);
+          accNu[mt][0][2 * o] = 0.f;
+        }
+    }
+  };
 
-  // ---- producer helper (lane 0 of the producer warp) ---------------------------------------------------------------
-  auto issue_stage = [&](int st) {
+  // ---- ring ---------------------------------------------------------------------------------------------
+  auto issue_stage = [&](int st) {  // one lane
     const int slot = st % NS;
-    const long long cs = c0 + (long long)st * R;
-    const int nv = (n_cells - st * R) < R ? (n_cells - st * R) : R;
+    const long long grpi = G0 + st;
+    const long long cs = grpi * R;
+    const int nv = (P.Nc - cs) < R ? (int)(P.Nc - cs) : R;
     const uint32_t row_bytes = (uint32_t)W * 4u;
-    const uint32_t bytes = (uint32_t)nv * (TABW * 4u + NMAT * row_bytes);
-    mbar_expect_tx(&full[slot], bytes);
-    bulk_g2s(s_tab + (size_t)slot * R * TABW, P.tab + cs * TABW, (uint32_t)nv * TABW * 4u, &full[slot]);
-    float* dstS = s_cnt + (size_t)slot * NMAT * R * W;
-    if ((long long)W == P.ld) {  // the tile spans whole rows: the nv rows are one contiguous block
-      bulk_g2s(dstS, P.S + cs * P.ld, (uint32_t)nv * row_bytes, &full[slot]);
-      if (VELO) bulk_g2s(dstS + (size_t)R * W, P.U + cs * P.ld, (uint32_t)nv * row_bytes, &full[slot]);
-    } else {
-      for (int rr = 0; rr < nv; ++rr) {
-        bulk_g2s(dstS + (size_t)rr * W, P.S + (cs + rr) * P.ld + g_base, row_bytes, &full[slot]);
-        if (VELO)
-          bulk_g2s(dstS + (size_t)(R + rr) * W, P.U + (cs + rr) * P.ld + g_base, row_bytes, &full[slot]);
-      }
+    mbar_expect_tx(&full[slot], (uint32_t)TABG * 4u + (uint32_t)nv * NMAT * row_bytes);
+    bulk_g2s(s_tab + (size_t)slot * TABG, P.tab + grpi * TABG, (uint32_t)TABG * 4u, &full[slot]);
+    float* dst = s_cnt + (size_t)slot * NMAT * R * RS;
+    for (int rr = 0; rr < nv; ++rr) {
+      bulk_g2s(dst + (size_t)rr * RS, P.S + (cs + rr) * P.ld + g_base, row_bytes, &full[slot]);
+      if (VELO) bulk_g2s(dst + (size_t)(R + rr) * RS, P.U + (cs + rr) * P.ld + g_base, row_bytes, &full[slot]);
+    }
+  };
+  // sum the per-warp cell partials of a finished stage in warp order and store them (whole warp)
+  float* const cellpart_t = P.cellpart + (long long)tile * P.Ncp * NQ;
+  auto flush_partials = [&](int st) {
+    if (lane < R * NQ) {
+      const float* src = s_part + (size_t)(st % NS) * nwarps * (R * NQ) + lane;
+      float s = 0.f;
+      for (int w = 0; w < nwarps; ++w) s += src[w * (R * NQ)];
+      cellpart_t[(G0 + st) * (R * NQ) + lane] = s;
     }
   };
 
   // Synchronisation: no CTA-wide barrier and no warp-to-warp waiting in steady state.
   //   full[s] : TMA bytes of the stage in slot s have landed            (1 arrival + complete_tx)
-  //   done[s] : every warp finished reading slot s                      (one arrival per warp)
-  // Refills are work-stolen: every warp polls (twice per stage, and while it waits for data) whether the
-  // slot of the next stage to issue has been released, and the warp that wins the CAS on s_next issues
-  // the copies.  All warps therefore run identical code and no warp is the designated straggler.
-  // (A dedicated producer warp would cost a whole 4-warp register allocation unit: 544 threads are
-  //  accounted as 640, which caps the consumers at 96 registers.)
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-  int* s_next = reinterpret_cast<int*>(mbar + 2 * NS);
+  //   done[s] : every warp finished with slot s (counts, table, partials) (one arrival per warp)
+  // Refills are work-stolen: every warp polls whether the slot of the next stage to issue has been released,
+  // and the warp that wins the CAS on s_next first drains the slot's cell partials, then issues the copies.
+  // (A dedicated producer warp would cost a whole 4-warp register allocation unit.)
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
@@ -215,17 +328,19 @@ __global__ void __launch_bounds__(max_threads(NP), 1) vcb_stream_kernel(const St
     const int v = *reinterpret_cast<volatile int*>(s_next);
     if (v >= n_stages) return;
     const int prev = v - NS;
-    int ready = mbar_test_wait(&done[prev % NS], (uint32_t)((prev / NS) & 1)) ? 1 : 0;
-    ready = __shfl_sync(0xffffffffu, ready, 0);
-    if (!ready) return;
+    if (!__all_sync(0xffffffffu, mbar_test_wait(&done[prev % NS], (uint32_t)((prev / NS) & 1)))) return;
     int won = 0;
     if (lane == 0) won = (atomicCAS(s_next, v, v + 1) == v) ? 1 : 0;
     won = __shfl_sync(0xffffffffu, won, 0);
-    if (won && lane == 0) issue_stage(v);
+    if (won) {
+      if (GRAD) flush_partials(prev);
+      __syncwarp();
+      if (lane == 0) issue_stage(v);
+    }
   };
-  float* const cellpart_w = P.cellpart + ((long long)tile * nwarps + warp) * P.Nc * NQ;
 
   const float2 one2 = f2s(1.f), neg1 = f2s(-1.f), l2e = f2s(kLog2e), eps2 = f2s(1e-5f);
+  int since_fold = 0;
 
   // ---- main loop ----------------------------------------------------------------------------------
   for (int st = 0; st < n_stages; ++st) {
@@ -237,239 +352,267 @@ __global__ void __launch_bounds__(max_threads(NP), 1) vcb_stream_kernel(const St
         if (++spins > (1u << 24)) __trap();
       }
     }
-    const int nv = (n_cells - st * R) < R ? (n_cells - st * R) : R;
-    const float* tabs = s_tab + (size_t)slot * R * TABW;
-    const float* cntS = s_cnt + (size_t)slot * NMAT * R * W;
-    float part[R * NQ];  // this thread's per-cell partial sums of the stage, [cell][q]
-#pragma unroll
-    for (int i = 0; i < R * NQ; ++i) part[i] = 0.f;
+    const long long cs = (G0 + st) * R;
+    const int nv = (P.Nc - cs) < R ? (int)(P.Nc - cs) : R;
+    const float* tb = s_tab + (size_t)slot * TABG;
+    const float* cnt = s_cnt + (size_t)slot * NMAT * R * RS;
+    const float4* tb4 = reinterpret_cast<const float4*>(tb);
+    float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
 
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      if (rr >= nv || P.debug_skip_compute) break;
-      // table row as broadcast float4 loads: T4[i] = {z_{2i}, z_{2i}, z_{2i+1}, z_{2i+1}}
-      const float4* T4 = reinterpret_cast<const float4*>(tabs + rr * TABW);
-      auto tpair = [&](int pi) -> float2 {  // pi is a compile-time constant after unrolling
-        const float4 v = T4[pi >> 1];
-        return (pi & 1) ? f2(v.z, v.w) : f2(v.x, v.y);
-      };
-      float pcf = 0.f, pphi = 0.f, pom = 0.f;
-      if (has_data) {
-        if (P.Nb > 0) {
-          const int b = __float_as_int(tabs[rr * TABW + 12 * H + 4]);
-          if (b != cur_b) {  // CTA-uniform: batch boundary (rare when samples are concatenated)
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-              const long long g0 = gj + 2 * p;
-              if (GRAD && cur_b >= 0) {
-                if (g0 < P.Ng) atomicAdd(&P.d_dnu[(long long)cur_b * P.Ng + g0], accNu[0][p].x);
-                if (g0 + 1 < P.Ng) atomicAdd(&P.d_dnu[(long long)cur_b * P.Ng + g0 + 1], accNu[0][p].y);
-                accNu[0][p] = zero2;
-              }
-              const float o0 = (g0 < P.Ng) ? P.dnu[(long long)b * P.Ng + g0] : 0.f;
-              const float o1 = (g0 + 1 < P.Ng) ? P.dnu[(long long)b * P.Ng + g0 + 1] : 0.f;
-              nu0c[p] = f2(nu[0][p].x - logf(-nr[p].x) + o0, nu[0][p].y - logf(-nr[p].y) + o1);
-            }
-            cur_b = b;
-          }
+    if (!P.debug_skip_compute) {
+      // ---- batch bookkeeping (CTA-uniform decisions: every warp reads the same table) -----------------
+      bool mixed = false;
+      int bc[2] = {0, 0};
+      if (P.Nb > 0) {
+        const int4 b0 = *reinterpret_cast<const int4*>(tb + TAIL + 8);
+        const int4 b1 = *reinterpret_cast<const int4*>(tb + TAIL + 12);
+        mixed = !(b0.x == b0.y && b0.x == b0.z && b0.x == b0.w && b0.x == b1.x && b0.x == b1.y && b0.x == b1.z &&
+                  b0.x == b1.w);
+        if (!mixed && b0.x != cur_b) {
+          if (GRAD) flush_batch();
+          cur_b = b0.x;
+          set_slot0(cur_b);
         }
-        const float2 om2 = tpair(P_OM);
-        const float2 cf2 = tpair(P_CF);
+        if (mixed) {  // rare (unsorted batches): offsets are added per element, d/ddnu goes through atomics
+          set_slot0(-1);
+          bc[0] = __float_as_int(tb[TAIL + 8 + q]);
+          bc[1] = __float_as_int(tb[TAIL + 12 + q]);
+        }
+      }
 
-        // forward contraction: eta' = etaS - ln r, d = nu.zeta', d2 = nu.zeta''
-        float2 eta[NP], d[NP], d2[NP];
+      // ---- forward contractions on the tensor pipe -------------------------------------------------------
+      float Ce[NT][4], Cd[NT][4], Cw[NT][4];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          eta[p] = add2(nu0c[p], cf2);
-          d[p] = zero2;
-          d2[p] = zero2;
+      for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Ce[mt][i] = Cd[mt][i] = Cw[mt][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const float4 bz = tb4[(SEC_F0 * KS + ks) * 32 + lane];
+#pragma unroll
+        for (int mt = 0; mt < NT; ++mt) mma3(Ce[mt], Ahi[mt][ks], Alo[mt][ks], bz);
+        if (NEED_D) {
+          const float4 bz1 = tb4[(SEC_F1 * KS + ks) * 32 + lane];
+#pragma unroll
+          for (int mt = 0; mt < NT; ++mt) mma3(Cd[mt], Ahi[mt][ks], Alo[mt][ks], bz1);
         }
+        if (NEED_E) {
+          const float4 bz2 = tb4[(SEC_F2 * KS + ks) * 32 + lane];
 #pragma unroll
-        for (int k = 1; k < K; ++k) {
-          const float2 z = tpair(k - 1);
-#pragma unroll
-          for (int p = 0; p < NP; ++p) eta[p] = fma2(nu[k][p], z, eta[p]);
-          if (GRAD || VELO) {
-            const float2 z1 = tpair(P_Z1 + k - 1);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) d[p] = (k == 1) ? mul2(nu[k][p], z1) : fma2(nu[k][p], z1, d[p]);
-          }
-          if (VELO && GRAD) {
-            const float2 z2 = tpair(P_Z2 + k - 1);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) d2[p] = (k == 1) ? mul2(nu[k][p], z2) : fma2(nu[k][p], z2, d2[p]);
-          }
+          for (int mt = 0; mt < NT; ++mt) mma3(Cw[mt], Ahi[mt][ks], Alo[mt][ks], bz2);
         }
+      }
+      float om[2] = {0.f, 0.f};
+      if (VELO) {
+        om[0] = tb[TAIL + q];
+        om[1] = tb[TAIL + q + 4];
+      }
 
-        float2 kS[NP], kU[NP];
-        {
-          const float* rowS = cntS + (size_t)rr * W + GPT * tid;
-          const float* rowU = cntS + (size_t)(R + rr) * W + GPT * tid;
-          if (NP == 2) {
-            const float4 a4 = *reinterpret_cast<const float4*>(rowS);
-            kS[0] = f2(a4.x, a4.y);
-            kS[NP - 1] = f2(a4.z, a4.w);
-            if (VELO) {
-              const float4 b4 = *reinterpret_cast<const float4*>(rowU);
-              kU[0] = f2(b4.x, b4.y);
-              kU[NP - 1] = f2(b4.z, b4.w);
-            }
-          } else {
-            kS[0] = *reinterpret_cast<const float2*>(rowS);
-            if (VELO) kU[0] = *reinterpret_cast<const float2*>(rowU);
-          }
-          if (!VELO) {
+      // ---- per-element negative-binomial terms ---------------------------------------------------------------
+      float2 Gg[NT][2], Gw[NT][2];  // backward A operands: [row tile][cell q / q+4] = gene pair
 #pragma unroll
-            for (int p = 0; p < NP; ++p) kU[p] = zero2;
-          }
-        }
-
-        float2 gE[NP], gd[NP];
+      for (int cc = 0; cc < 2; ++cc) {
+        const bool cvalid = (q + 4 * cc) < nv;
+        const float2 om2 = f2s(om[cc]);
         float2 pcf2 = zero2, pphi2 = zero2, pom2 = zero2;
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          const float2 y = mul2(eta[p], l2e);
-          const float2 u = ex2_2(y);
-          const float2 s = add2(u, one2);
-          const float2 LS = lg2_2(s);
-          accAS[p] = fma2(kS[p], fma2(LS, neg1, y), accAS[p]);
-          accLS[p] = add2(accLS[p], LS);
-          float2 g = zero2;
-          if (GRAD) g = mul2(fma2(nr[p], u, kS[p]), rcp_2(s));
-          if (LGINLINE) {
-            float2 psi, lg;
-            lg.x = lgamma_terms_inline(-nr[p].x, kS[p].x, psi.x);
-            lg.y = lgamma_terms_inline(-nr[p].y, kS[p].y, psi.y);
-            accAS[p] = fma2(lg, l2e, accAS[p]);
-            accPsi[p] = add2(accPsi[p], psi);
+        for (int p = 0; p < NPAIR; ++p) {
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = s4;
+          if (gvalid[p] && cvalid) {  // rows of missing cells / columns past the pitch hold stale bytes
+            s4 = *reinterpret_cast<const float4*>(cnt + (size_t)(q + 4 * cc) * RS + gl[p]);
+            if (VELO) u4 = *reinterpret_cast<const float4*>(cnt + (size_t)(R + q + 4 * cc) * RS + gl[p]);
           }
-          gd[p] = zero2;
-          if (VELO) {
-            const float2 a = fma2(d[p], om2, gam[p]);
-            const float2 m = add2(f2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), eps2);
-            const float2 mb = mul2(m, invb[p]);
-            const float2 uU = mul2(u, mb);
-            const float2 sU = add2(uU, one2);
-            const float2 LU = lg2_2(sU);
-            const float2 lmb = lg2_2(mb);
-            accAU[p] = fma2(kU[p], fma2(LU, neg1, add2(y, lmb)), accAU[p]);
-            accLU[p] = add2(accLU[p], LU);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int mt = 2 * p + t;
+            const float2 kS = t ? f2(s4.z, s4.w) : f2(s4.x, s4.y);
+            const float2 kU = t ? f2(u4.z, u4.w) : f2(u4.x, u4.y);
+            float2 eta = f2(Ce[mt][cc], Ce[mt][2 + cc]);
+            const float2 d = f2(Cd[mt][cc], Cd[mt][2 + cc]);
+            if (mixed) {
+              const long long g0 = gene_of(mt, 0), brow = (long long)bc[cc] * P.Ng;
+              if (g0 < P.Ng) eta.x += P.dnu[brow + g0];
+              if (g0 + 1 < P.Ng) eta.y += P.dnu[brow + g0 + 1];
+            }
+            const float2 y = mul2(eta, l2e);
+            const float2 u = ex2_2(y);
+            const float2 s = add2(u, one2);
+            const float2 LS = lg2_2(s);
+            accAS[mt] = fma2(kS, fma2(LS, neg1, y), accAS[mt]);
+            accLS[mt] = add2(accLS[mt], LS);
             if (LGINLINE) {
               float2 psi, lg;
-              lg.x = lgamma_terms_inline(-nr[p].x, kU[p].x, psi.x);
-              lg.y = lgamma_terms_inline(-nr[p].y, kU[p].y, psi.y);
-              accAU[p] = fma2(lg, l2e, accAU[p]);
-              accPsi[p] = add2(accPsi[p], psi);
+              lg.x = lgamma_terms_inline(-nr[mt].x, kS.x, psi.x);
+              lg.y = lgamma_terms_inline(-nr[mt].y, kS.y, psi.y);
+              accAS[mt] = fma2(lg, l2e, accAS[mt]);
+              accPsi[mt] = add2(accPsi[mt], psi);
+            }
+            float2 g = zero2, w = zero2;
+            if (VELO) {
+              const float2 a = fma2(d, om2, gam[mt]);
+              const float2 m = add2(f2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), eps2);
+              const float2 mb = mul2(m, invb[mt]);
+              const float2 uU = mul2(u, mb);
+              const float2 sU = add2(uU, one2);
+              const float2 LU = lg2_2(sU);
+              const float2 lmb = lg2_2(mb);
+              accAU[mt] = fma2(kU, fma2(LU, neg1, add2(y, lmb)), accAU[mt]);
+              accLU[mt] = add2(accLU[mt], LU);
+              if (LGINLINE) {
+                float2 psi, lg;
+                lg.x = lgamma_terms_inline(-nr[mt].x, kU.x, psi.x);
+                lg.y = lgamma_terms_inline(-nr[mt].y, kU.y, psi.y);
+                accAU[mt] = fma2(lg, l2e, accAU[mt]);
+                accPsi[mt] = add2(accPsi[mt], psi);
+              }
+              if (GRAD) {
+                const float2 sUm = mul2(sU, m);
+                const float2 rc = rcp_2(mul2(s, sUm));  // one MUFU for 1/s and 1/(sU m)
+                const float2 inv_s = mul2(rc, sUm), inv_sUm = mul2(rc, s);
+                const float2 gS = mul2(fma2(nr[mt], u, kS), inv_s);
+                const float2 w0 = mul2(fma2(nr[mt], uU, kU), inv_sUm);
+                const float2 gU = mul2(w0, m);
+                w = f2(a.x > 0.f ? w0.x : 0.f, a.y > 0.f ? w0.y : 0.f);
+                g = add2(gS, gU);
+                accGU[mt] = add2(accGU[mt], gU);
+                pom2 = fma2(w, d, pom2);
+                pphi2 = fma2(w, f2(Cw[mt][cc], Cw[mt][2 + cc]), pphi2);
+              }
+            } else if (GRAD) {
+              g = mul2(fma2(nr[mt], u, kS), rcp_2(s));
             }
             if (GRAD) {
-              const float2 w0 = mul2(fma2(nr[p], uU, kU[p]), rcp_2(mul2(sU, m)));
-              const float2 gU = mul2(w0, m);
-              const float2 w = f2(a.x > 0.f ? w0.x : 0.f, a.y > 0.f ? w0.y : 0.f);
-              g = add2(g, gU);
-              gd[p] = mul2(w, om2);
-              accGU[p] = add2(accGU[p], gU);
-              accW[p] = add2(accW[p], w);
-              pom2 = fma2(w, d[p], pom2);
-              pphi2 = fma2(gd[p], d2[p], pphi2);
+              pcf2 = add2(pcf2, g);
+              pphi2 = fma2(g, d, pphi2);
+              if (mixed && cvalid) {
+                const long long g0 = gene_of(mt, 0), brow = (long long)bc[cc] * P.Ng;
+                if (g0 < P.Ng) atomicAdd(&P.d_dnu[brow + g0], g.x);
+                if (g0 + 1 < P.Ng) atomicAdd(&P.d_dnu[brow + g0 + 1], g.y);
+              }
             }
-          }
-          gE[p] = g;
-          if (GRAD) {
-            pcf2 = add2(pcf2, g);
-            pphi2 = fma2(g, d[p], pphi2);
-            accNu[0][p] = add2(accNu[0][p], g);
+            Gg[mt][cc] = g;
+            Gw[mt][cc] = w;
           }
         }
-        if (GRAD) {
-#pragma unroll
-          for (int k = 1; k < K; ++k) {
-            const float2 z = tpair(k - 1);
-#pragma unroll
-            for (int p = 0; p < NP; ++p) accNu[k][p] = fma2(gE[p], z, accNu[k][p]);
-            if (VELO) {
-              const float2 z1 = tpair(P_Z1 + k - 1);
-#pragma unroll
-              for (int p = 0; p < NP; ++p) accNu[k][p] = fma2(gd[p], z1, accNu[k][p]);
-            }
-          }
-          pcf = pcf2.x + pcf2.y;
-          pphi = pphi2.x + pphi2.y;
-          pom = pom2.x + pom2.y;
-        }
+        pcf[cc] = pcf2.x + pcf2.y;
+        pphi[cc] = pphi2.x + pphi2.y;
+        pom[cc] = pom2.x + pom2.y;
       }
-      if (rr == R / 2 - 1) poll_refill();
+      poll_refill();
+
+      // ---- backward contractions on the tensor pipe: accT[gene][slot] += sum_cells G[gene][cell] Z[cell][slot] --
       if (GRAD) {
-        part[rr * NQ + 0] = pcf;
-        part[rr * NQ + 1] = pphi;
-        if (VELO) part[rr * NQ + 2] = pom;
-      }
-    }
-    if (GRAD) {
-      // reduce-scatter over the stage's R cells: after log2(R) halving steps the lanes whose bits
-      // [4 .. 5-log2 R] spell cell c hold that cell's NQ sums over their lane group; finish with an
-      // all-reduce inside the group and let the group's first lane store them.
-      int n = R * NQ;
-      int off = 16;
 #pragma unroll
-      for (int step = 0; step < 5; ++step, off >>= 1) {
-        if ((R >> step) > 1) {
-          n >>= 1;
-          const bool upper = (lane & off) != 0;
+        for (int nt = 0; nt < KS; ++nt) {
+          float4 bz = tb4[(SEC_B0 * KS + nt) * 32 + lane];
+          if (mixed && nt == 0 && grp == 0) bz.x = bz.y = 0.f;  // constant column off: d/ddnu went through atomics
 #pragma unroll
-          for (int i = 0; i < n; ++i) {
-            const float keep = upper ? part[i + n] : part[i];
-            const float send = upper ? part[i] : part[i + n];
-            part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          for (int mt = 0; mt < NT; ++mt) {
+            uint32_t ghi[4], glo[4];
+            split_trunc(Gg[mt][0].x, ghi[0], glo[0]);
+            split_trunc(Gg[mt][0].y, ghi[1], glo[1]);
+            split_trunc(Gg[mt][1].x, ghi[2], glo[2]);
+            split_trunc(Gg[mt][1].y, ghi[3], glo[3]);
+            mma3(accT[mt][nt], ghi, glo, bz);
           }
-        } else {
+          if (VELO) {
+            const float4 bz1 = tb4[(SEC_B1 * KS + nt) * 32 + lane];
 #pragma unroll
-          for (int i = 0; i < NQ; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], off);
+            for (int mt = 0; mt < NT; ++mt) {
+              uint32_t whi[4], wlo[4];
+              split_trunc(Gw[mt][0].x, whi[0], wlo[0]);
+              split_trunc(Gw[mt][0].y, whi[1], wlo[1]);
+              split_trunc(Gw[mt][1].x, whi[2], wlo[2]);
+              split_trunc(Gw[mt][1].y, whi[3], wlo[3]);
+              mma3(accT[mt][nt], whi, wlo, bz1);
+            }
+          }
+        }
+        if (++since_fold == kFlushEvery) {
+          fold_acc();
+          since_fold = 0;
         }
       }
-      constexpr int LPC = 32 / R;  // lanes per cell group
-      const int cell = lane / LPC;
-      if ((lane % LPC) == 0 && cell < nv) {
-        float* dst = cellpart_w + (c0 + (long long)st * R + cell) * NQ;
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) dst[i] = part[i];
-      }
-    } else {
-      __syncwarp();
+      if (mixed) set_slot0(cur_b);
     }
-    if (lane == 0) mbar_arrive(&done[slot]);  // this warp no longer needs the slot
+
+    if (GRAD) {
+      // sums over the warp's genes: the lane holds cells q and q+4; first swap halves so that lanes 0-15 keep
+      // cell q and lanes 16-31 cell q+4, then add over the remaining grp bits
+      const bool up = (lane & 16) != 0;
+      float v[NQ];
+      v[0] = (up ? pcf[1] : pcf[0]) + __shfl_xor_sync(0xffffffffu, up ? pcf[0] : pcf[1], 16);
+      v[1] = (up ? pphi[1] : pphi[0]) + __shfl_xor_sync(0xffffffffu, up ? pphi[0] : pphi[1], 16);
+      if (VELO) v[NQ - 1] = (up ? pom[1] : pom[0]) + __shfl_xor_sync(0xffffffffu, up ? pom[0] : pom[1], 16);
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 8);
+        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 4);
+      }
+      if ((lane & 12) == 0) {
+        float* dst = s_part + ((size_t)slot * nwarps + warp) * (R * NQ) + (q + 4 * (lane >> 4)) * NQ;
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) dst[i] = v[i];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[slot]);  // this warp no longer needs the slot (release: partials are visible)
     poll_refill();
   }
 
+  // ---- drain: the last ring-depth stages were never refilled, their cell partials are still parked -----------
+  if (GRAD) {
+    __syncthreads();
+    const int first = n_stages > NS ? n_stages - NS : 0;
+    for (int st = first + warp; st < n_stages; st += nwarps) flush_partials(st);
+  }
+
   // ---- flush per-gene partial sums ----------------------------------------------------------------
-  if (has_data) {
-    if (GRAD && P.Nb > 0 && cur_b >= 0) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        const long long g0 = gj + 2 * p;
-        if (g0 < P.Ng) atomicAdd(&P.d_dnu[(long long)cur_b * P.Ng + g0], accNu[0][p].x);
-        if (g0 + 1 < P.Ng) atomicAdd(&P.d_dnu[(long long)cur_b * P.Ng + g0 + 1], accNu[0][p].y);
-      }
+  if (GRAD) {
+    if (P.Nb > 0) {
+      flush_batch();
+    } else {
+      fold_acc();
     }
-    constexpr int ROWS = gene_rows(H);
-    float* gp = P.genepart + ((long long)split * ROWS) * P.ld + gj;
-    auto st4 = [&](int row, const float2* v) {
+  }
+  constexpr int ROWS = gene_rows(H);
+  float* gp = P.genepart + ((long long)split * ROWS) * P.ld;
+  auto lane_sum4 = [&](float2 v) -> float2 {  // over the 4 lanes (cells) that share a gene pair
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, 1);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, 2);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);
+    return v;
+  };
 #pragma unroll
-      for (int p = 0; p < NP; ++p) *reinterpret_cast<float2*>(gp + (long long)row * P.ld + 2 * p) = v[p];
+  for (int mt = 0; mt < NT; ++mt) {
+    const bool ok = gvalid[mt >> 1];
+    const long long g0 = gene_of(mt, 0);  // even: the pair (g0, g0+1) is one aligned float2
+    auto put = [&](int row, float2 v) {
+      v = lane_sum4(v);
+      if (ok && q == 0) *reinterpret_cast<float2*>(gp + (long long)row * P.ld + g0) = v;
     };
-    st4(ROW_AS, accAS);
-    st4(ROW_LS, accLS);
+    put(ROW_AS, accAS[mt]);
+    put(ROW_LS, accLS[mt]);
     if (VELO) {
-      st4(ROW_AU, accAU);
-      st4(ROW_LU, accLU);
-      if (GRAD) {
-        st4(ROW_GU, accGU);
-        st4(ROW_W, accW);
-      }
+      put(ROW_AU, accAU[mt]);
+      put(ROW_LU, accLU[mt]);
+      if (GRAD) put(ROW_GU, accGU[mt]);
     }
-    if (LGINLINE) st4(ROW_PSI, accPsi);
-    if (GRAD) {
+    if (LGINLINE) put(ROW_PSI, accPsi[mt]);
+    if (GRAD && ok) {
+      // accumulator fragment: c0 (gene g0, slot 2q) c1 (g0, 2q+1) c2 (g0+1, 2q) c3 (g0+1, 2q+1)
 #pragma unroll
-      for (int k = 0; k < K; ++k) st4(ROW_DNU + k, accNu[k]);
+      for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int slot_k = 8 * nt + 2 * q + (i & 1);
+          const long long g = g0 + (i >> 1);
+          if (slot_k < K)
+            gp[(long long)(ROW_DNU + slot_k) * P.ld + g] = accNu[mt][nt][i];
+          else if (VELO && slot_k == K)
+            gp[(long long)ROW_W * P.ld + g] = accNu[mt][nt][i];
+        }
     }
   }
 }
