@@ -93,23 +93,31 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
   __syncwarp();
   const int grp = lane >> 2, q = lane & 3;
   float4* out = reinterpret_cast<float4*>(P.tab + group * P.tabg);
-  auto emit = [&](int sec_out, int ks, float x0, float x1) {
-    uint32_t h0, l0, h1, l1;
-    split_tf32(x0, h0, l0);
-    split_tf32(x1, h1, l1);
+  // one table entry: {TF32 hi of the main MMA's b0, b1; BF16x2 {y0, y1} and {lo y0, lo y1} of the cross-term MMA}
+  auto emit = [&](int sec_out, int ks, float x0, float x1, float y0, float y1) {
     out[(sec_out * KS + ks) * 32 + lane] =
-        make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+        make_float4(__uint_as_float(tf32_rna(x0)), __uint_as_float(tf32_rna(x1)), __uint_as_float(pack_bf16(y0, y1)),
+                    __uint_as_float(pack_bf16(tf32_lo(y0), tf32_lo(y1))));
   };
   const int fc = fwd_cell(grp);
   for (int ks = 0; ks < KS; ++ks) {
-    // forward B fragments: b0 (k = q, n = grp), b1 (k = q+4, n = grp); column n is cell fwd_cell(n)
-    emit(SEC_F0, ks, sv[warp][0][fc][8 * ks + q], sv[warp][0][fc][8 * ks + q + 4]);
-    emit(SEC_F1, ks, sv[warp][1][fc][8 * ks + q], sv[warp][1][fc][8 * ks + q + 4]);
-    // backward B fragments: b0 (k = cell q, n = slot grp), b1 (k = cell q+4, n = slot grp)
-    emit(SEC_B0, ks, sv[warp][3][q][8 * ks + grp], sv[warp][3][q + 4][8 * ks + grp]);
+    // forward: main b0 (k = q, n = grp), b1 (k = q+4); cross k = 2q, 2q+1 (and their lo parts at 2q+8, 2q+9);
+    // column n is cell fwd_cell(n)
+    auto fwd = [&](int sec_out, int sec) {
+      const float* z = sv[warp][sec][fc] + 8 * ks;
+      emit(sec_out, ks, z[q], z[q + 4], z[2 * q], z[2 * q + 1]);
+    };
+    // backward: k runs over cells: main b0 (cell q, n = slot grp), b1 (cell q+4); cross pairs the same two cells
+    auto bwd = [&](int sec_out, int sec) {
+      const float z0 = sv[warp][sec][q][8 * ks + grp], z1 = sv[warp][sec][q + 4][8 * ks + grp];
+      emit(sec_out, ks, z0, z1, z0, z1);
+    };
+    fwd(SEC_F0, 0);
+    fwd(SEC_F1, 1);
+    bwd(SEC_B0, 3);
     if (P.velo) {
-      emit(SEC_F2, ks, sv[warp][2][fc][8 * ks + q], sv[warp][2][fc][8 * ks + q + 4]);
-      emit(SEC_B1, ks, sv[warp][4][q][8 * ks + grp], sv[warp][4][q + 4][8 * ks + grp]);
+      fwd(SEC_F2, 2);
+      bwd(SEC_B1, 4);
     }
   }
   if (lane < 16) P.tab[group * P.tabg + table_tail(H, P.velo != 0) + lane] = s_tail[warp][lane];

@@ -5,10 +5,12 @@
 // (eta = nu.zeta, d = nu.zeta', nu.zeta'') and two backward (d/dnu += gE zeta + w omega zeta'): 31 of the
 // 61 fp32 operations of the element.  The fp32 pipe, not HBM, bounded the first version of this kernel
 // (DESIGN.md section 4), so those contractions now run on the tensor pipe as warp-level m16n8k8 TF32 MMAs
-// (SASS HMMA.1688.F32.TF32) with the 3xTF32 split (x = hi + lo, drop lo*lo) that keeps fp32-level accuracy;
-// the fp32 pipe keeps the negative-binomial terms, the MUFU pipe the 5 transcendentals.  K = 2H+1 <= 7 fits
-// one 8-wide k-step together with one spare slot that carries the per-cell size factor forward and
-// sum_c w (= d/dgamma) backward.  (tcgen05 is the wrong tool here: its operands live in shared memory, and
+// with the split x = hi + lo that keeps fp32-level accuracy: A.B ~ Ahi.Bhi (one m16n8k8 TF32 MMA, SASS
+// HMMA.1688.F32.TF32) + [Alo | A].[B ; Blo] (both cross terms in ONE m16n8k16 BF16 MMA, HMMA.16816.F32.BF16:
+// they are 2^-11 of the product, so 8 mantissa bits suffice); lo*lo is dropped.  The fp32 pipe keeps the
+// negative-binomial terms, the MUFU pipe the 5 transcendentals.  The harmonics 1..2H (<= 6) fit one 8-wide
+// k-step together with one spare slot that carries the per-cell size factor forward and sum_c w (= d/dgamma)
+// backward; the constant term nu_0 - ln r (+ batch offset) is added in fp32 (it is the largest addend).  (tcgen05 is the wrong tool here: its operands live in shared memory, and
 // the backward operand gE is produced in registers by the same threads that consume the forward result.)
 //
 // Mapping (genes are the contiguous axis of the counts, preprocessing.py:193-194):
@@ -19,15 +21,17 @@
 //     kernel (no atomics on the hot path).  The forward accumulator fragment of a row tile IS the backward
 //     A fragment ({c0,c2,c1,c3} -> {a0,a1,a2,a3}) once the forward B columns are permuted (column 2j -> cell j,
 //     2j+1 -> cell j+4), so nothing is transposed or shuffled between the two GEMMs;
-//   * cells stream through a shared-memory ring filled by the TMA engine with 1-D bulk copies (cp.async.bulk
-//     + mbarrier complete_tx); a stage = one 8-cell group: 8 count rows of S and of U (row pitch = tile + 8
-//     floats, which makes the per-lane LDS.128 of 4 genes conflict-free) plus the group's operand table built
-//     by vcb_cell_tables_kernel: the B fragments of every MMA, already split hi/lo and stored in lane order;
+//   * counts stream through a shared-memory ring of kCountDepth 8-cell groups filled with 128-bit cp.async
+//     (LDGSTS.128, zero-filled outside the matrix): every warp loads exactly the 32 genes x 8 cells x {S, U} per
+//     group it consumes itself (a warp instruction covers 4 rows x one full 128-byte line), so the count stream
+//     needs no barrier beyond cp.async.wait_group + __syncwarp and a slow warp never delays another warp's loads;
+//   * the operand table of a group (built by vcb_cell_tables_kernel: the B fragments of every MMA, already split
+//     and stored in lane order, 2.6 KB) is shared by all warps and staged by the TMA engine (cp.async.bulk +
+//     mbarrier complete_tx) in a second, deeper ring; its issue rotates over the warps;
 //   * per-cell sums (d/dphi, d/dcf, d/domega run over genes, i.e. over grp lanes and warps) are reduced
 //     once per group with 9 shuffles, parked per warp in shared memory and summed in a fixed order by the
-//     warp that later refills the slot (deterministic, no atomics);
-//   * no CTA-wide barrier and no warp waits for another warp in steady state: full[]/done[] mbarriers only,
-//     refills are work-stolen.
+//     warp that re-issues the slot's table copy (deterministic, no atomics);
+//   * no CTA-wide barrier and no warp waits for another warp in steady state: full[]/done[] mbarriers only.
 //
 // Arithmetic per (cell, gene), SURVEY.md Appendix A, in units of mu/r and base-2 logs so that every
 // transcendental is a single MUFU op and the n r log r terms cancel analytically:
@@ -41,10 +45,10 @@
 namespace vcb {
 
 constexpr int kGroupCells = 8;  // cells per ring stage = the n extent (forward) / k extent (backward) of the MMAs
-constexpr int kMaxStages = 8;   // ring depth is chosen on the host to fill shared memory, up to this
-constexpr int kRowPad = 8;      // count rows sit at a pitch of tile+8 floats in shared memory
+constexpr int kCountDepth = 6;  // count groups in flight per thread (6 x 32 KB per 512-thread CTA)
+constexpr int kMaxStages = 16;  // the table ring is as deep as the rest of shared memory allows, up to this
 constexpr int kFlushEvery = 8;  // d/dnu MMA accumulators are folded into fp32 registers every so many groups
-constexpr int kSmemHeader = 256;
+constexpr int kSmemHeader = 512;
 
 // A warp owns 32*NPAIR genes.  NPAIR = 1: up to 512 threads/CTA at <= 128 registers; NPAIR = 2: up to 256.
 __host__ __device__ constexpr int max_threads(int NPAIR) { return NPAIR == 1 ? 512 : 256; }
@@ -53,8 +57,9 @@ __host__ __device__ constexpr int max_threads(int NPAIR) { return NPAIR == 1 ? 5
 enum GeneRow { ROW_AS = 0, ROW_LS = 1, ROW_AU = 2, ROW_LU = 3, ROW_GU = 4, ROW_W = 5, ROW_PSI = 6, ROW_DNU = 7 };
 __host__ __device__ constexpr int gene_rows(int H) { return ROW_DNU + 2 * H + 1; }
 
-// Operand table of one 8-cell group: sections of [k-step][lane][4] floats = {hi b0, hi b1, lo b0, lo b1},
-// then omega[8] and batch id[8].  Slots of a k-step row: 0 -> constant, 1..2H -> harmonics, 2H+1 -> spare.
+// Operand table of one 8-cell group: sections of [k-step][lane][4] words = {TF32 b0, TF32 b1 of the main MMA,
+// BF16x2 b0, BF16x2 b1 of the cross-term MMA}, then omega[8] and batch id[8].
+// Slots of a k-step row: 0 -> constant, 1..2H -> harmonics, 2H+1 -> spare.
 enum TabSection { SEC_F0 = 0, SEC_F1 = 1, SEC_B0 = 2, SEC_F2 = 3, SEC_B1 = 4 };
 __host__ __device__ constexpr int ksteps(int H) { return (2 * H + 2 + 7) / 8; }
 __host__ __device__ constexpr int table_sections(bool velo) { return velo ? 5 : 3; }
@@ -79,7 +84,7 @@ struct StreamParams {
   long long Nc, Ng, ld, Ncp;
   int n_split;
   int Nb;
-  int n_ring;              // ring depth
+  int n_ring;              // depth of the table ring
   int debug_skip_compute;  // profiling aid: stream the tiles but skip the arithmetic
 };
 
@@ -89,8 +94,7 @@ struct StreamSmem {
 
 __host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, int nwarps, int npair, int n_ring) {
   StreamSmem L;
-  const int WT = 32 * npair * nwarps;
-  int off = kSmemHeader;  // mbarriers + the refill cursor
+  int off = kSmemHeader;  // mbarriers
   L.part_off = off;
   off += n_ring * nwarps * kGroupCells * (velo ? 3 : 2) * 4;
   off = (off + 127) / 128 * 128;
@@ -98,7 +102,7 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, int n
   off += n_ring * table_group_floats(H, velo) * 4;
   off = (off + 127) / 128 * 128;
   L.cnt_off = off;
-  off += n_ring * (velo ? 2 : 1) * kGroupCells * (WT + kRowPad) * 4;
+  off += kCountDepth * (velo ? 2 : 1) * 2 * npair * (32 * nwarps) * 16;  // [depth][matrix][cell q / q+4][pair][thread] x 16 B
   L.total = off;
   return L;
 }
@@ -113,36 +117,68 @@ __device__ __forceinline__ float2 ex2_2(float2 a) { return f2(ex2_approx(a.x), e
 __device__ __forceinline__ float2 lg2_2(float2 a) { return f2(lg2_approx(a.x), lg2_approx(a.y)); }
 __device__ __forceinline__ float2 rcp_2(float2 a) { return f2(rcp_approx(a.x), rcp_approx(a.y)); }
 
-// ---- TF32 tensor-core helpers ---------------------------------------------------------------------------
+// ---- cp.async (LDGSTS.128): 16 bytes global -> shared, zero-filled when src_bytes == 0 ---------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- tensor-core helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
-// x = hi + lo with hi, lo representable in TF32 (lo rounded): the operands of the 3xTF32 scheme
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_rna(x);
-  lo = tf32_rna(x - __uint_as_float(hi));
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(tf32_rna(x)); }
+// two floats -> one register of two BF16; `k_even` lands in the low half (the lower k index of an MMA operand pair)
+__device__ __forceinline__ uint32_t pack_bf16(float k_even, float k_odd) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(k_odd), "f"(k_even));
+  return r;
 }
-// hot-path split: hi by truncation (one LOP), lo = x - hi exactly (the MMA ignores lo's 13 low mantissa bits)
-__device__ __forceinline__ void split_trunc(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-// D(16x8) += A(16x8, row) * B(8x8, col).  Fragments (grp = lane/4, q = lane%4):
+// Fragments (grp = lane/4, q = lane%4).  m16n8k8 TF32:
 //   a0 (grp, q)  a1 (grp+8, q)  a2 (grp, q+4)  a3 (grp+8, q+4);  b0 (k=q, n=grp)  b1 (k=q+4, n=grp);
 //   c0 (grp, 2q)  c1 (grp, 2q+1)  c2 (grp+8, 2q)  c3 (grp+8, 2q+1)
+// m16n8k16 BF16 (two k per register, lower k in the low half):
+//   a0 (grp, k=2q,2q+1)  a1 (grp+8, 2q,2q+1)  a2 (grp, 2q+8,2q+9)  a3 (grp+8, 2q+8,2q+9);
+//   b0 (k=2q,2q+1, n=grp)  b1 (k=2q+8,2q+9, n=grp);  c as above
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// C += (Ahi + Alo)(Bhi + Blo) without the lo*lo term, small terms first
-__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const float4 b) {
-  mma_tf32(c, alo, __float_as_uint(b.x), __float_as_uint(b.y));
-  mma_tf32(c, ahi, __float_as_uint(b.z), __float_as_uint(b.w));
-  mma_tf32(c, ahi, __float_as_uint(b.x), __float_as_uint(b.y));
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// C += A.B with A = amain (TF32 hi) and the cross terms folded into across = [Alo | A] (BF16), small terms first;
+// b = one table entry {main b0, main b1, cross b0, cross b1}
+__device__ __forceinline__ void mma_split(float (&c)[4], const uint32_t (&amain)[4], const uint32_t (&across)[4],
+                                          const float4 b) {
+  mma_bf16(c, across, __float_as_uint(b.z), __float_as_uint(b.w));
+  mma_tf32(c, amain, __float_as_uint(b.x), __float_as_uint(b.y));
+}
+// backward A operands of one row tile from the gene-pair values of the cells q (v0) and q+4 (v1)
+__device__ __forceinline__ void split_operand(const float2 v0, const float2 v1, uint32_t (&amain)[4],
+                                              uint32_t (&across)[4]) {
+  amain[0] = __float_as_uint(v0.x) & 0xffffe000u;
+  amain[1] = __float_as_uint(v0.y) & 0xffffe000u;
+  amain[2] = __float_as_uint(v1.x) & 0xffffe000u;
+  amain[3] = __float_as_uint(v1.y) & 0xffffe000u;
+  const float2 l0 = __fadd2_rn(v0, make_float2(-__uint_as_float(amain[0]), -__uint_as_float(amain[1])));
+  const float2 l1 = __fadd2_rn(v1, make_float2(-__uint_as_float(amain[2]), -__uint_as_float(amain[3])));
+  across[0] = pack_bf16(l0.x, l1.x);
+  across[1] = pack_bf16(l0.y, l1.y);
+  across[2] = pack_bf16(v0.x, v1.x);
+  across[3] = pack_bf16(v0.y, v1.y);
 }
 
 template <int H, bool VELO, bool GRAD, bool LGINLINE, int NPAIR>
@@ -153,6 +189,8 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   constexpr int NMAT = VELO ? 2 : 1;
   constexpr int NQ = VELO ? 3 : 2;
   constexpr int R = kGroupCells;
+  constexpr int D = kCountDepth;
+  constexpr int NLD = NMAT * 2 * NPAIR;  // 16-byte count loads per thread and group: [matrix][cell q / q+4][pair]
   constexpr int TABG = table_group_floats(H, VELO);
   constexpr int TAIL = table_tail(H, VELO);
   constexpr bool NEED_D = GRAD || VELO;
@@ -167,7 +205,6 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   const int tile = blockIdx.x;
   const int split = blockIdx.y;
   const int WT = 32 * NPAIR * nwarps;  // genes per CTA tile
-  const int RS = WT + kRowPad;         // shared-memory pitch of a count row, floats
   const long long g_base = (long long)tile * WT;
   const long long rem = P.ld - g_base;
   const int W = (int)(rem < (long long)WT ? rem : (long long)WT);  // genes of this tile that exist in a row
@@ -175,10 +212,9 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* full = mbar;  // [kMaxStages] each; roles documented where they are initialised
   uint64_t* done = mbar + kMaxStages;
-  int* s_next = reinterpret_cast<int*>(mbar + 2 * kMaxStages);
   float* s_part = reinterpret_cast<float*>(smem_raw + L.part_off);
   float* s_tab = reinterpret_cast<float*>(smem_raw + L.tab_off);
-  float* s_cnt = reinterpret_cast<float*>(smem_raw + L.cnt_off);
+  float4* s_cnt = reinterpret_cast<float4*>(smem_raw + L.cnt_off) + tid;  // this thread's column of the count ring
 
   // this CTA's cell groups
   const long long n_groups = P.Ncp / R;
@@ -190,34 +226,40 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   // pair p, gene j in 0..3: g = g_base + (warp*NPAIR + p)*32 + 4*grp + j; row tile mt = 2p + (j>>1) holds
   // gene j in fragment rows grp (j even) and grp+8 (j odd).
   int gl[NPAIR];       // tile-local index of the lane's first gene of pair p
-  bool gvalid[NPAIR];  // the lane's 16 bytes exist in the shared-memory rows
+  bool gvalid[NPAIR];  // the lane's 4 genes of pair p lie inside the row pitch
 #pragma unroll
   for (int p = 0; p < NPAIR; ++p) {
     gl[p] = (warp * NPAIR + p) * 32 + 4 * grp;
     gvalid[p] = gl[p] < W;
   }
   auto gene_of = [&](int mt, int odd) -> long long { return g_base + gl[mt >> 1] + 2 * (mt & 1) + odd; };
-  auto lnr_of = [&](long long g) -> float { return g < P.Ng ? -logf(P.shape_inv[g]) : 0.f; };  // ln r
-  // value of the forward A operand (gene g, slot): [nu0 - ln r (+ dnu[b]), nu_1..nu_2H, 1, 0...]
-  auto a_value = [&](long long g, int slot, int b) -> float {
-    if (g >= P.Ng) return slot == 0 ? -1e30f : 0.f;  // padding gene: eta = -inf makes every contribution zero
-    if (slot == 0) {
-      float v = P.nu[g * K] - lnr_of(g);
-      if (b >= 0) v += P.dnu[(long long)b * P.Ng + g];
-      return v;
-    }
-    if (slot < K) return P.nu[g * K + slot];
-    return slot == K ? 1.f : 0.f;
+  // forward A operand (gene g, slot): [0, nu_1..nu_2H, 1, 0...]; a padding gene is all zero
+  auto a_value = [&](long long g, int slot) -> float {
+    if (g >= P.Ng || slot == 0 || slot > K) return 0.f;
+    return slot == K ? 1.f : P.nu[g * K + slot];
   };
-  uint32_t Ahi[NT][KS][4], Alo[NT][KS][4];
-  float2 nr[NT], gam[NT], invb[NT];
+  // the constant addend nu_0 - ln r (+ batch offset); -inf on a padding gene makes every contribution zero
+  auto const_term = [&](long long g, int b) -> float {
+    if (g >= P.Ng) return -1e30f;
+    float v = P.nu[g * K] + logf(P.shape_inv[g]);
+    if (b >= 0) v += P.dnu[(long long)b * P.Ng + g];
+    return v;
+  };
+  uint32_t Amain[NT][KS][4], Across[NT][KS][4];
+  float2 nu0c[NT], nr[NT], gam[NT], invb[NT];
 #pragma unroll
   for (int mt = 0; mt < NT; ++mt) {
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
+    for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        split_tf32(a_value(gene_of(mt, i & 1), 8 * ks + q + 4 * (i >> 1), -1), Ahi[mt][ks][i], Alo[mt][ks][i]);
+      for (int i = 0; i < 4; ++i) Amain[mt][ks][i] = tf32_rna(a_value(gene_of(mt, i & 1), 8 * ks + q + 4 * (i >> 1)));
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const float x0 = a_value(gene_of(mt, o), 8 * ks + 2 * q), x1 = a_value(gene_of(mt, o), 8 * ks + 2 * q + 1);
+        Across[mt][ks][o] = pack_bf16(tf32_lo(x0), tf32_lo(x1));
+        Across[mt][ks][2 + o] = pack_bf16(x0, x1);
+      }
+    }
     float rs[2], gs[2], ibs[2];
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
@@ -230,15 +272,11 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     nr[mt] = f2(-rs[0], -rs[1]);
     gam[mt] = f2(gs[0], gs[1]);
     invb[mt] = f2(ibs[0], ibs[1]);
+    nu0c[mt] = f2(const_term(gene_of(mt, 0), -1), const_term(gene_of(mt, 1), -1));
   }
-  // slot 0 of the A operand carries the batch offset of the current batch (only the q == 0 lanes hold slot 0)
-  auto set_slot0 = [&](int b) {
-    if (q == 0) {
+  auto set_batch = [&](int b) {
 #pragma unroll
-      for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-        for (int o = 0; o < 2; ++o) split_tf32(a_value(gene_of(mt, o), 0, b), Ahi[mt][0][o], Alo[mt][0][o]);
-    }
+    for (int mt = 0; mt < NT; ++mt) nu0c[mt] = f2(const_term(gene_of(mt, 0), b), const_term(gene_of(mt, 1), b));
   };
   int cur_b = -1;
 
@@ -281,81 +319,116 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     }
   };
 
-  // ---- ring ---------------------------------------------------------------------------------------------
-  auto issue_stage = [&](int st) {  // one lane
-    const int slot = st % NS;
-    const long long grpi = G0 + st;
-    const long long cs = grpi * R;
-    const int nv = (P.Nc - cs) < R ? (int)(P.Nc - cs) : R;
-    const uint32_t row_bytes = (uint32_t)W * 4u;
-    mbar_expect_tx(&full[slot], (uint32_t)TABG * 4u + (uint32_t)nv * NMAT * row_bytes);
-    bulk_g2s(s_tab + (size_t)slot * TABG, P.tab + grpi * TABG, (uint32_t)TABG * 4u, &full[slot]);
-    float* dst = s_cnt + (size_t)slot * NMAT * R * RS;
-    for (int rr = 0; rr < nv; ++rr) {
-      bulk_g2s(dst + (size_t)rr * RS, P.S + (cs + rr) * P.ld + g_base, row_bytes, &full[slot]);
-      if (VELO) bulk_g2s(dst + (size_t)(R + rr) * RS, P.U + (cs + rr) * P.ld + g_base, row_bytes, &full[slot]);
+  // ---- count ring: warp-private cp.async pipeline -----------------------------------------------------------
+  // Consumer lane (grp, q) reads slot (d, j) = s_cnt[(d*NLD + j)*nthr], j = (matrix*2 + cc)*NPAIR + p: the 16 bytes
+  // of its 4 genes at cell q + 4cc.  The LOADS use another lane mapping: 8 consecutive lanes fetch one full
+  // 128-byte line (row lane/8, 16-byte chunk lane%8) -- with the consumer mapping a quarter-warp would touch 4
+  // rows x 32 B, four times the memory requests (measured: 4.5 vs 6.9 TB/s, tools/ubench_tma.cu) -- and write
+  // into the slot of the lane that will consume them, so a __syncwarp() separates loads from reads.  Loads outside
+  // the matrix (cells >= Nc, genes past the pitch) are zero-filled by the copy itself: the consumer never masks.
+  const int l_row = lane >> 3, l_chunk = lane & 7;
+  float4* const s_cnt_ld = reinterpret_cast<float4*>(smem_raw + L.cnt_off) + (warp * 32 + 4 * l_chunk + l_row);
+  const float* cnt_src[NPAIR];
+#pragma unroll
+  for (int p = 0; p < NPAIR; ++p) {
+    const int lgl = (warp * NPAIR + p) * 32 + 4 * l_chunk;
+    cnt_src[p] = lgl < W ? P.S + g_base + lgl : nullptr;
+  }
+  const long long u_minus_s =  // byte distance between the two matrices: one row pointer serves both
+      VELO ? (long long)reinterpret_cast<uintptr_t>(P.U) - (long long)reinterpret_cast<uintptr_t>(P.S) : 0;
+  auto load_counts = [&](int st, int d) {  // stage st into depth slot d (= st % D, tracked by the caller)
+    if (st < n_stages) {
+      const long long cs = (G0 + st) * R;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const long long c = cs + 4 * cc + l_row;
+        const bool cok = c < P.Nc;
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) {
+          const bool ok = cok && cnt_src[p] != nullptr;
+          const float* src = ok ? cnt_src[p] + c * P.ld : P.S;
+#pragma unroll
+          for (int mat = 0; mat < NMAT; ++mat)
+            cp_async16(s_cnt_ld + (size_t)(d * NLD + (mat * 2 + cc) * NPAIR + p) * nthr,
+                       (mat && ok) ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + u_minus_s) : src,
+                       ok ? 16u : 0u);
+        }
+      }
     }
-  };
-  // sum the per-warp cell partials of a finished stage in warp order and store them (whole warp)
-  float* const cellpart_t = P.cellpart + (long long)tile * P.Ncp * NQ;
-  auto flush_partials = [&](int st) {
-    if (lane < R * NQ) {
-      const float* src = s_part + (size_t)(st % NS) * nwarps * (R * NQ) + lane;
-      float s = 0.f;
-      for (int w = 0; w < nwarps; ++w) s += src[w * (R * NQ)];
-      cellpart_t[(G0 + st) * (R * NQ) + lane] = s;
-    }
+    cp_async_commit();  // one group per stage, empty past the end: wait_group counts stay uniform
   };
 
-  // Synchronisation: no CTA-wide barrier and no warp-to-warp waiting in steady state.
-  //   full[s] : TMA bytes of the stage in slot s have landed            (1 arrival + complete_tx)
-  //   done[s] : every warp finished with slot s (counts, table, partials) (one arrival per warp)
-  // Refills are work-stolen: every warp polls whether the slot of the next stage to issue has been released,
-  // and the warp that wins the CAS on s_next first drains the slot's cell partials, then issues the copies.
-  // (A dedicated producer warp would cost a whole 4-warp register allocation unit.)
+  // ---- table ring (TMA) and the per-cell partial sums -------------------------------------------------------
+  //   full[s] : the operand table in slot s has landed              (arrive.expect_tx + complete_tx)
+  //   done[s] : every warp finished with slot s (table, partials)   (one arrival per warp)
+  // Stage v is issued by warp v % nwarps, which first drains the slot's cell partials (summed in warp order:
+  // deterministic).  Each warp walks its own stages with a private cursor: no shared cursor, no CAS.
+  // The ring is deep (up to 16 groups), so a refill is never urgent and nobody spins on done[].
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&done[s], (uint32_t)nwarps);
     }
     mbar_fence_init();
-    int st = 0;
-    for (; st < NS && st < n_stages; ++st) issue_stage(st);
-    *s_next = st;
   }
   __syncthreads();
-  auto poll_refill = [&]() {  // warp-uniform; never blocks
-    const int v = *reinterpret_cast<volatile int*>(s_next);
-    if (v >= n_stages) return;
-    const int prev = v - NS;
-    if (!__all_sync(0xffffffffu, mbar_test_wait(&done[prev % NS], (uint32_t)((prev / NS) & 1)))) return;
-    int won = 0;
-    if (lane == 0) won = (atomicCAS(s_next, v, v + 1) == v) ? 1 : 0;
-    won = __shfl_sync(0xffffffffu, won, 0);
-    if (won) {
-      if (GRAD) flush_partials(prev);
-      __syncwarp();
-      if (lane == 0) issue_stage(v);
+  float* const cellpart_t = P.cellpart + (long long)tile * P.Ncp * NQ;
+  // sum the per-warp cell partials of a finished stage in warp order and store them (whole warp)
+  auto flush_partials = [&](int st, int slot) {
+    if (lane < R * NQ) {
+      const float* src = s_part + (size_t)slot * nwarps * (R * NQ) + lane;
+      float s = 0.f;
+      for (int w = 0; w < nwarps; ++w) s += src[w * (R * NQ)];
+      cellpart_t[(G0 + st) * (R * NQ) + lane] = s;
     }
   };
+  int i_next = warp, i_slot = warp % NS, i_k = warp / NS;  // issue cursor over this warp's stages: stage = i_k*NS + i_slot
+  int consumed = 0;                                        // stages this warp has finished
+  auto issue_table = [&]() -> bool {  // warp-uniform; never blocks; true if a stage was issued
+    if (i_next >= n_stages) return false;
+    if (i_k > 0) {  // the slot held stage i_next - NS: wait until every warp has left it, then drain its partials
+      // A parity wait only distinguishes adjacent phases: do not look at done[] before this warp itself has
+      // arrived for stage i_next - NS (with fewer slots than warps its next stage is two phases ahead).
+      if (i_next - NS >= consumed) return false;
+      int ready = 0;
+      if (lane == 0) ready = mbar_test_wait(&done[i_slot], (uint32_t)((i_k - 1) & 1)) ? 1 : 0;
+      if (!__shfl_sync(0xffffffffu, ready, 0)) return false;
+      if (GRAD) flush_partials(i_next - NS, i_slot);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      mbar_expect_tx(&full[i_slot], (uint32_t)TABG * 4u);
+      bulk_g2s(s_tab + (size_t)i_slot * TABG, P.tab + (G0 + i_next) * TABG, (uint32_t)TABG * 4u, &full[i_slot]);
+    }
+    i_next += nwarps;
+    i_slot += nwarps;
+    while (i_slot >= NS) {
+      i_slot -= NS;
+      ++i_k;
+    }
+    return true;
+  };
+  while (i_k == 0 && issue_table()) {}  // prologue: the slots are fresh
+#pragma unroll
+  for (int s = 0; s < D; ++s) load_counts(s, s);
 
   const float2 one2 = f2s(1.f), neg1 = f2s(-1.f), l2e = f2s(kLog2e), eps2 = f2s(1e-5f);
   int since_fold = 0;
+  int c_slot = 0, c_phase = 0, c_d = 0;  // consumer cursor: table slot / parity, count depth slot
 
   // ---- main loop ----------------------------------------------------------------------------------
   for (int st = 0; st < n_stages; ++st) {
-    const int slot = st % NS;
     {
       uint32_t spins = 0;
-      while (!__all_sync(0xffffffffu, mbar_try_wait(&full[slot], (uint32_t)((st / NS) & 1)))) {
-        poll_refill();
+      while (!__all_sync(0xffffffffu, mbar_try_wait(&full[c_slot], (uint32_t)c_phase))) {
+        issue_table();
         if (++spins > (1u << 24)) __trap();
       }
     }
-    const long long cs = (G0 + st) * R;
-    const int nv = (P.Nc - cs) < R ? (int)(P.Nc - cs) : R;
-    const float* tb = s_tab + (size_t)slot * TABG;
-    const float* cnt = s_cnt + (size_t)slot * NMAT * R * RS;
+    cp_async_wait<D - 1>();  // this lane's loads of stage st have landed ...
+    __syncwarp();            // ... and so have the other lanes' (counts never cross a warp)
+    const float* tb = s_tab + (size_t)c_slot * TABG;
+    const float4* cnt = s_cnt + (size_t)c_d * NLD * nthr;
     const float4* tb4 = reinterpret_cast<const float4*>(tb);
     float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
 
@@ -371,10 +444,9 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
         if (!mixed && b0.x != cur_b) {
           if (GRAD) flush_batch();
           cur_b = b0.x;
-          set_slot0(cur_b);
+          set_batch(cur_b);
         }
         if (mixed) {  // rare (unsorted batches): offsets are added per element, d/ddnu goes through atomics
-          set_slot0(-1);
           bc[0] = __float_as_int(tb[TAIL + 8 + q]);
           bc[1] = __float_as_int(tb[TAIL + 12 + q]);
         }
@@ -390,16 +462,16 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
       for (int ks = 0; ks < KS; ++ks) {
         const float4 bz = tb4[(SEC_F0 * KS + ks) * 32 + lane];
 #pragma unroll
-        for (int mt = 0; mt < NT; ++mt) mma3(Ce[mt], Ahi[mt][ks], Alo[mt][ks], bz);
+        for (int mt = 0; mt < NT; ++mt) mma_split(Ce[mt], Amain[mt][ks], Across[mt][ks], bz);
         if (NEED_D) {
           const float4 bz1 = tb4[(SEC_F1 * KS + ks) * 32 + lane];
 #pragma unroll
-          for (int mt = 0; mt < NT; ++mt) mma3(Cd[mt], Ahi[mt][ks], Alo[mt][ks], bz1);
+          for (int mt = 0; mt < NT; ++mt) mma_split(Cd[mt], Amain[mt][ks], Across[mt][ks], bz1);
         }
         if (NEED_E) {
           const float4 bz2 = tb4[(SEC_F2 * KS + ks) * 32 + lane];
 #pragma unroll
-          for (int mt = 0; mt < NT; ++mt) mma3(Cw[mt], Ahi[mt][ks], Alo[mt][ks], bz2);
+          for (int mt = 0; mt < NT; ++mt) mma_split(Cw[mt], Amain[mt][ks], Across[mt][ks], bz2);
         }
       }
       float om[2] = {0.f, 0.f};
@@ -412,27 +484,22 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
       float2 Gg[NT][2], Gw[NT][2];  // backward A operands: [row tile][cell q / q+4] = gene pair
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const bool cvalid = (q + 4 * cc) < nv;
         const float2 om2 = f2s(om[cc]);
         float2 pcf2 = zero2, pphi2 = zero2, pom2 = zero2;
 #pragma unroll
         for (int p = 0; p < NPAIR; ++p) {
-          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = s4;
-          if (gvalid[p] && cvalid) {  // rows of missing cells / columns past the pitch hold stale bytes
-            s4 = *reinterpret_cast<const float4*>(cnt + (size_t)(q + 4 * cc) * RS + gl[p]);
-            if (VELO) u4 = *reinterpret_cast<const float4*>(cnt + (size_t)(R + q + 4 * cc) * RS + gl[p]);
-          }
+          const float4 s4 = cnt[(size_t)(cc * NPAIR + p) * nthr];
+          const float4 u4 = VELO ? cnt[(size_t)((2 + cc) * NPAIR + p) * nthr] : s4;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int mt = 2 * p + t;
             const float2 kS = t ? f2(s4.z, s4.w) : f2(s4.x, s4.y);
             const float2 kU = t ? f2(u4.z, u4.w) : f2(u4.x, u4.y);
-            float2 eta = f2(Ce[mt][cc], Ce[mt][2 + cc]);
+            float2 eta = add2(f2(Ce[mt][cc], Ce[mt][2 + cc]), nu0c[mt]);
             const float2 d = f2(Cd[mt][cc], Cd[mt][2 + cc]);
-            if (mixed) {
-              const long long g0 = gene_of(mt, 0), brow = (long long)bc[cc] * P.Ng;
-              if (g0 < P.Ng) eta.x += P.dnu[brow + g0];
-              if (g0 + 1 < P.Ng) eta.y += P.dnu[brow + g0 + 1];
+            if (mixed) {  // nu0c carries the offset of cur_b: swap it for the cell's own batch
+              const long long g0 = gene_of(mt, 0);
+              eta = add2(f2(Ce[mt][cc], Ce[mt][2 + cc]), f2(const_term(g0, bc[cc]), const_term(g0 + 1, bc[cc])));
             }
             const float2 y = mul2(eta, l2e);
             const float2 u = ex2_2(y);
@@ -484,7 +551,7 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
             if (GRAD) {
               pcf2 = add2(pcf2, g);
               pphi2 = fma2(g, d, pphi2);
-              if (mixed && cvalid) {
+              if (mixed && (G0 + st) * R + q + 4 * cc < P.Nc) {
                 const long long g0 = gene_of(mt, 0), brow = (long long)bc[cc] * P.Ng;
                 if (g0 < P.Ng) atomicAdd(&P.d_dnu[brow + g0], g.x);
                 if (g0 + 1 < P.Ng) atomicAdd(&P.d_dnu[brow + g0 + 1], g.y);
@@ -498,34 +565,20 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
         pphi[cc] = pphi2.x + pphi2.y;
         pom[cc] = pom2.x + pom2.y;
       }
-      poll_refill();
 
       // ---- backward contractions on the tensor pipe: accT[gene][slot] += sum_cells G[gene][cell] Z[cell][slot] --
       if (GRAD) {
 #pragma unroll
-        for (int nt = 0; nt < KS; ++nt) {
-          float4 bz = tb4[(SEC_B0 * KS + nt) * 32 + lane];
-          if (mixed && nt == 0 && grp == 0) bz.x = bz.y = 0.f;  // constant column off: d/ddnu went through atomics
+        for (int mt = 0; mt < NT; ++mt) {
+          uint32_t gm[4], gx[4], wm[4], wx[4];
+          split_operand(Gg[mt][0], Gg[mt][1], gm, gx);
+          if (VELO) split_operand(Gw[mt][0], Gw[mt][1], wm, wx);
 #pragma unroll
-          for (int mt = 0; mt < NT; ++mt) {
-            uint32_t ghi[4], glo[4];
-            split_trunc(Gg[mt][0].x, ghi[0], glo[0]);
-            split_trunc(Gg[mt][0].y, ghi[1], glo[1]);
-            split_trunc(Gg[mt][1].x, ghi[2], glo[2]);
-            split_trunc(Gg[mt][1].y, ghi[3], glo[3]);
-            mma3(accT[mt][nt], ghi, glo, bz);
-          }
-          if (VELO) {
-            const float4 bz1 = tb4[(SEC_B1 * KS + nt) * 32 + lane];
-#pragma unroll
-            for (int mt = 0; mt < NT; ++mt) {
-              uint32_t whi[4], wlo[4];
-              split_trunc(Gw[mt][0].x, whi[0], wlo[0]);
-              split_trunc(Gw[mt][0].y, whi[1], wlo[1]);
-              split_trunc(Gw[mt][1].x, whi[2], wlo[2]);
-              split_trunc(Gw[mt][1].y, whi[3], wlo[3]);
-              mma3(accT[mt][nt], whi, wlo, bz1);
-            }
+          for (int nt = 0; nt < KS; ++nt) {
+            float4 bz = tb4[(SEC_B0 * KS + nt) * 32 + lane];
+            if (mixed && nt == 0 && grp == 0) bz.x = bz.y = bz.z = 0.f;  // constant column off: d/ddnu went through atomics
+            mma_split(accT[mt][nt], gm, gx, bz);
+            if (VELO) mma_split(accT[mt][nt], wm, wx, tb4[(SEC_B1 * KS + nt) * 32 + lane]);
           }
         }
         if (++since_fold == kFlushEvery) {
@@ -533,7 +586,6 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
           since_fold = 0;
         }
       }
-      if (mixed) set_slot0(cur_b);
     }
 
     if (GRAD) {
@@ -550,21 +602,29 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
         v[i] += __shfl_xor_sync(0xffffffffu, v[i], 4);
       }
       if ((lane & 12) == 0) {
-        float* dst = s_part + ((size_t)slot * nwarps + warp) * (R * NQ) + (q + 4 * (lane >> 4)) * NQ;
+        float* dst = s_part + ((size_t)c_slot * nwarps + warp) * (R * NQ) + (q + 4 * (lane >> 4)) * NQ;
 #pragma unroll
         for (int i = 0; i < NQ; ++i) dst[i] = v[i];
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&done[slot]);  // this warp no longer needs the slot (release: partials are visible)
-    poll_refill();
+    if (lane == 0) mbar_arrive(&done[c_slot]);  // this warp no longer needs the slot (release: partials are visible)
+    if (++c_slot == NS) {
+      c_slot = 0;
+      c_phase ^= 1;
+    }
+    consumed = st + 1;
+    load_counts(st + D, c_d);  // refill the count slot this thread has just consumed
+    if (++c_d == D) c_d = 0;
+    issue_table();
   }
+  cp_async_wait<0>();
 
-  // ---- drain: the last ring-depth stages were never refilled, their cell partials are still parked -----------
+  // ---- drain: the last ring-depth stages were never re-issued, their cell partials are still parked ----------
   if (GRAD) {
     __syncthreads();
     const int first = n_stages > NS ? n_stages - NS : 0;
-    for (int st = first + warp; st < n_stages; st += nwarps) flush_partials(st);
+    for (int st = first + warp; st < n_stages; st += nwarps) flush_partials(st, st % NS);
   }
 
   // ---- flush per-gene partial sums ----------------------------------------------------------------
