@@ -39,7 +39,7 @@ constexpr int kTabSlots = 16;  // 8 * ksteps(VCB_MAX_HARMONICS)
 __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const CellParams P) {
   // per warp and cell: [0] forward eta operand, [1] zeta', [2] omega*zeta'', [3] backward zeta, [4] omega*zeta'
   __shared__ float sv[kTabWarps][5][kGroupCells][kTabSlots];
-  __shared__ float s_tail[kTabWarps][16];
+  __shared__ float s_tail[kTabWarps][20];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long group = (long long)blockIdx.x * kTabWarps + warp;
   if (group >= P.n_groups) return;
@@ -120,7 +120,15 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
       bwd(SEC_B1, 4);
     }
   }
-  if (lane < 16) P.tab[group * P.tabg + table_tail(H, P.velo != 0) + lane] = s_tail[warp][lane];
+  if (lane == 0) {  // the group's batch id if its 8 cells agree, else -1 (the streaming kernel's fast-path test)
+    int b = __float_as_int(s_tail[warp][8]);
+    for (int i = 1; i < kGroupCells; ++i)
+      if (__float_as_int(s_tail[warp][8 + i]) != b) b = -1;
+    s_tail[warp][16] = __int_as_float(b);
+    s_tail[warp][17] = s_tail[warp][18] = s_tail[warp][19] = 0.f;
+  }
+  __syncwarp();
+  if (lane < 20) P.tab[group * P.tabg + table_tail(H, P.velo != 0) + lane] = s_tail[warp][lane];
 }
 
 // ======================================================================================================

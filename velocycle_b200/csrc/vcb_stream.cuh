@@ -47,7 +47,6 @@ namespace vcb {
 constexpr int kGroupCells = 8;  // cells per ring stage = the n extent (forward) / k extent (backward) of the MMAs
 constexpr int kCountDepth = 6;  // count groups in flight per thread (6 x 32 KB per 512-thread CTA)
 constexpr int kMaxStages = 16;  // the table ring is as deep as the rest of shared memory allows, up to this
-constexpr int kFlushEvery = 8;  // d/dnu MMA accumulators are folded into fp32 registers every so many groups
 constexpr int kSmemHeader = 512;
 
 // A warp owns 32*NPAIR genes.  NPAIR = 1: up to 512 threads/CTA at <= 128 registers; NPAIR = 2: up to 256.
@@ -58,13 +57,13 @@ enum GeneRow { ROW_AS = 0, ROW_LS = 1, ROW_AU = 2, ROW_LU = 3, ROW_GU = 4, ROW_W
 __host__ __device__ constexpr int gene_rows(int H) { return ROW_DNU + 2 * H + 1; }
 
 // Operand table of one 8-cell group: sections of [k-step][lane][4] words = {TF32 b0, TF32 b1 of the main MMA,
-// BF16x2 b0, BF16x2 b1 of the cross-term MMA}, then omega[8] and batch id[8].
+// BF16x2 b0, BF16x2 b1 of the cross-term MMA}, then omega[8], batch id[8] and {the batch id if all 8 agree else -1, 0, 0, 0}.
 // Slots of a k-step row: 0 -> constant, 1..2H -> harmonics, 2H+1 -> spare.
 enum TabSection { SEC_F0 = 0, SEC_F1 = 1, SEC_B0 = 2, SEC_F2 = 3, SEC_B1 = 4 };
 __host__ __device__ constexpr int ksteps(int H) { return (2 * H + 2 + 7) / 8; }
 __host__ __device__ constexpr int table_sections(bool velo) { return velo ? 5 : 3; }
 __host__ __device__ constexpr int table_tail(int H, bool velo) { return table_sections(velo) * ksteps(H) * 128; }
-__host__ __device__ constexpr int table_group_floats(int H, bool velo) { return table_tail(H, velo) + 16; }
+__host__ __device__ constexpr int table_group_floats(int H, bool velo) { return table_tail(H, velo) + 20; }
 // forward B column n of a group holds cell fwd_cell(n): the accumulator columns {2q, 2q+1} of a lane are then
 // the cells {q, q+4} that the same lane must supply as backward A columns
 __host__ __device__ constexpr int fwd_cell(int n) { return (n >> 1) + 4 * (n & 1); }
@@ -89,7 +88,7 @@ struct StreamParams {
 };
 
 struct StreamSmem {
-  int part_off, tab_off, cnt_off, total;  // byte offsets inside dynamic shared memory
+  int part_off, gene_off, tab_off, cnt_off, total;  // byte offsets inside dynamic shared memory
 };
 
 __host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, int nwarps, int npair, int n_ring) {
@@ -98,6 +97,8 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, int n
   L.part_off = off;
   off += n_ring * nwarps * kGroupCells * (velo ? 3 : 2) * 4;
   off = (off + 127) / 128 * 128;
+  L.gene_off = off;  // per-gene parameters: [warp][row tile][2][grp] float4
+  off += nwarps * 2 * npair * 2 * 8 * 16;
   L.tab_off = off;
   off += n_ring * table_group_floats(H, velo) * 4;
   off = (off + 127) / 128 * 128;
@@ -118,9 +119,8 @@ __device__ __forceinline__ float2 lg2_2(float2 a) { return f2(lg2_approx(a.x), l
 __device__ __forceinline__ float2 rcp_2(float2 a) { return f2(rcp_approx(a.x), rcp_approx(a.y)); }
 
 // ---- cp.async (LDGSTS.128): 16 bytes global -> shared, zero-filled when src_bytes == 0 ---------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
-               : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -181,6 +181,11 @@ __device__ __forceinline__ void split_operand(const float2 v0, const float2 v1, 
   across[3] = pack_bf16(v0.y, v1.y);
 }
 
+template <bool B>
+struct BoolTag {
+  static constexpr bool value = B;
+};
+
 template <int H, bool VELO, bool GRAD, bool LGINLINE, int NPAIR>
 __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const StreamParams P) {
   constexpr int K = 2 * H + 1;
@@ -209,12 +214,10 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   const long long rem = P.ld - g_base;
   const int W = (int)(rem < (long long)WT ? rem : (long long)WT);  // genes of this tile that exist in a row
   const StreamSmem L = stream_smem_layout(H, VELO, nwarps, NPAIR, NS);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* full = mbar;  // [kMaxStages] each; roles documented where they are initialised
-  uint64_t* done = mbar + kMaxStages;
+  const uint32_t full0 = smem_u32(smem_raw);     // shared-window addresses of full[0] / done[0] ([kMaxStages] each;
+  const uint32_t done0 = full0 + 8 * kMaxStages;  // roles documented where they are initialised)
   float* s_part = reinterpret_cast<float*>(smem_raw + L.part_off);
   float* s_tab = reinterpret_cast<float*>(smem_raw + L.tab_off);
-  float4* s_cnt = reinterpret_cast<float4*>(smem_raw + L.cnt_off) + tid;  // this thread's column of the count ring
 
   // this CTA's cell groups
   const long long n_groups = P.Ncp / R;
@@ -246,7 +249,9 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     return v;
   };
   uint32_t Amain[NT][KS][4], Across[NT][KS][4];
-  float2 nu0c[NT], nr[NT], gam[NT], invb[NT];
+  // Dispersion, kinetics and the constant term live in shared memory (the 4 lanes of a grp share them; one
+  // broadcast LDS.128 per row tile brings {-r, c0} and {gamma, 1/beta} as gene pairs): 16 registers fewer.
+  float4* const s_gene = reinterpret_cast<float4*>(smem_raw + L.gene_off) + (size_t)warp * (NT * 2 * 8) + grp;
 #pragma unroll
   for (int mt = 0; mt < NT; ++mt) {
 #pragma unroll
@@ -260,53 +265,51 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
         Across[mt][ks][2 + o] = pack_bf16(x0, x1);
       }
     }
-    float rs[2], gs[2], ibs[2];
+    if (q == 0) {
+      float rs[2], gs[2], ibs[2];
 #pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      const long long g = gene_of(mt, o);
-      const bool ok = g < P.Ng;
-      rs[o] = ok ? 1.0f / P.shape_inv[g] : 1.f;
-      gs[o] = (ok && VELO) ? P.gamma[g] : 1.f;
-      ibs[o] = (ok && VELO) ? expf(-P.logbeta[g]) : 1.f;
+      for (int o = 0; o < 2; ++o) {
+        const long long g = gene_of(mt, o);
+        const bool ok = g < P.Ng;
+        rs[o] = ok ? 1.0f / P.shape_inv[g] : 1.f;
+        gs[o] = (ok && VELO) ? P.gamma[g] : 1.f;
+        ibs[o] = (ok && VELO) ? expf(-P.logbeta[g]) : 1.f;
+      }
+      s_gene[(mt * 2 + 0) * 8] = make_float4(-rs[0], -rs[1], const_term(gene_of(mt, 0), -1), const_term(gene_of(mt, 1), -1));
+      s_gene[(mt * 2 + 1) * 8] = make_float4(gs[0], gs[1], ibs[0], ibs[1]);
     }
-    nr[mt] = f2(-rs[0], -rs[1]);
-    gam[mt] = f2(gs[0], gs[1]);
-    invb[mt] = f2(ibs[0], ibs[1]);
-    nu0c[mt] = f2(const_term(gene_of(mt, 0), -1), const_term(gene_of(mt, 1), -1));
   }
+  __syncwarp();
   auto set_batch = [&](int b) {
+    __syncwarp();
+    if (q == 0) {
 #pragma unroll
-    for (int mt = 0; mt < NT; ++mt) nu0c[mt] = f2(const_term(gene_of(mt, 0), b), const_term(gene_of(mt, 1), b));
+      for (int mt = 0; mt < NT; ++mt) {
+        float4 v = s_gene[(mt * 2 + 0) * 8];
+        v.z = const_term(gene_of(mt, 0), b);
+        v.w = const_term(gene_of(mt, 1), b);
+        s_gene[(mt * 2 + 0) * 8] = v;
+      }
+    }
+    __syncwarp();
   };
   int cur_b = -1;
 
   const float2 zero2 = f2s(0.f);
   float2 accAS[NT], accLS[NT], accAU[NT], accLU[NT], accGU[NT], accPsi[NT];
-  float accNu[NT][KS][4], accT[NT][KS][4];  // d/dnu fragments: fp32 running sums and the MMA accumulators
+  // d/dnu fragments.  Tensor-core accumulation truncates, and a long chain of small addends into a large sum
+  // would drift: the MMA accumulators start from zero in every group and are added here with fp32 rounding.
+  float accNu[NT][KS][4];
 #pragma unroll
   for (int mt = 0; mt < NT; ++mt) {
     accAS[mt] = accLS[mt] = accAU[mt] = accLU[mt] = accGU[mt] = accPsi[mt] = zero2;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) accNu[mt][ks][i] = accT[mt][ks][i] = 0.f;
+      for (int i = 0; i < 4; ++i) accNu[mt][ks][i] = 0.f;
   }
-  // Tensor-core accumulation truncates; a long chain of small addends into a large sum would drift, so the
-  // MMA accumulators only ever hold kFlushEvery groups and are folded into fp32 registers with rounding.
-  auto fold_acc = [&]() {
-#pragma unroll
-    for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          accNu[mt][ks][i] += accT[mt][ks][i];
-          accT[mt][ks][i] = 0.f;
-        }
-  };
   // batch boundary: the constant column of d/dnu (slot 0: lanes q == 0, c0 / c2) is the batch's d/ddnu
   auto flush_batch = [&]() {
-    fold_acc();
     if (q == 0 && cur_b >= 0) {
 #pragma unroll
       for (int mt = 0; mt < NT; ++mt)
@@ -327,33 +330,58 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   // into the slot of the lane that will consume them, so a __syncwarp() separates loads from reads.  Loads outside
   // the matrix (cells >= Nc, genes past the pitch) are zero-filled by the copy itself: the consumer never masks.
   const int l_row = lane >> 3, l_chunk = lane & 7;
-  float4* const s_cnt_ld = reinterpret_cast<float4*>(smem_raw + L.cnt_off) + (warp * 32 + 4 * l_chunk + l_row);
-  const float* cnt_src[NPAIR];
+  const uint32_t s_cnt_ld = smem_u32(reinterpret_cast<float4*>(smem_raw + L.cnt_off) + (warp * 32 + 4 * l_chunk + l_row));
+  const uint32_t slot_bytes = (uint32_t)nthr * 16u;  // distance between two of a thread's slots
+  const uint32_t half_off = (uint32_t)(16 * P.ld);   // bytes from row r to row r+4 (ld <= 2^24)
+  const long long row_step = 4ll * R * P.ld;         // bytes from one group to the next
+  // Row pointers of the next stage to load.  A lane whose genes lie past the row pitch copies 0 bytes (= zero
+  // fill) from a clamped, valid address, so the steady-state path has no per-lane branches.
+  const char* ldS[NPAIR];
+  const char* ldU[NPAIR];
+  uint32_t ld_sz[NPAIR];
 #pragma unroll
   for (int p = 0; p < NPAIR; ++p) {
     const int lgl = (warp * NPAIR + p) * 32 + 4 * l_chunk;
-    cnt_src[p] = lgl < W ? P.S + g_base + lgl : nullptr;
+    const long long off = (G0 * R + l_row) * P.ld + g_base + (lgl < W ? lgl : 0);
+    ld_sz[p] = lgl < W ? 16u : 0u;
+    ldS[p] = reinterpret_cast<const char*>(P.S + off);
+    ldU[p] = reinterpret_cast<const char*>((VELO ? P.U : P.S) + off);
   }
-  const long long u_minus_s =  // byte distance between the two matrices: one row pointer serves both
-      VELO ? (long long)reinterpret_cast<uintptr_t>(P.U) - (long long)reinterpret_cast<uintptr_t>(P.S) : 0;
-  auto load_counts = [&](int st, int d) {  // stage st into depth slot d (= st % D, tracked by the caller)
-    if (st < n_stages) {
-      const long long cs = (G0 + st) * R;
+  long long ld_rows_left = P.Nc - G0 * R;  // rows from the next stage's first row to the end of the matrix
+  int ld_left = n_stages;                  // stages still to load
+  auto load_counts = [&](int d) {          // next stage into depth slot d (stages are loaded in order)
+    if (ld_left > 0) {
+      uint32_t dst = s_cnt_ld + (uint32_t)d * (NLD * slot_bytes);
+      if (ld_rows_left >= R) {  // CTA-uniform; only the very last group of the matrix can be ragged
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const long long c = cs + 4 * cc + l_row;
-        const bool cok = c < P.Nc;
+        for (int mat = 0; mat < NMAT; ++mat)
 #pragma unroll
-        for (int p = 0; p < NPAIR; ++p) {
-          const bool ok = cok && cnt_src[p] != nullptr;
-          const float* src = ok ? cnt_src[p] + c * P.ld : P.S;
+          for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
-          for (int mat = 0; mat < NMAT; ++mat)
-            cp_async16(s_cnt_ld + (size_t)(d * NLD + (mat * 2 + cc) * NPAIR + p) * nthr,
-                       (mat && ok) ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(src) + u_minus_s) : src,
-                       ok ? 16u : 0u);
-        }
+            for (int p = 0; p < NPAIR; ++p) {
+              cp_async16(dst, (mat ? ldU[p] : ldS[p]) + (cc ? half_off : 0u), ld_sz[p]);
+              dst += slot_bytes;
+            }
+      } else {
+#pragma unroll
+        for (int mat = 0; mat < NMAT; ++mat)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+            for (int p = 0; p < NPAIR; ++p) {
+              const bool ok = 4 * cc + l_row < ld_rows_left;
+              cp_async16(dst, ok ? (mat ? ldU[p] : ldS[p]) + (cc ? half_off : 0u) : reinterpret_cast<const char*>(P.S),
+                         ok ? ld_sz[p] : 0u);
+              dst += slot_bytes;
+            }
       }
+#pragma unroll
+      for (int p = 0; p < NPAIR; ++p) {
+        ldS[p] += row_step;
+        ldU[p] += row_step;
+      }
+      ld_rows_left -= R;
+      --ld_left;
     }
     cp_async_commit();  // one group per stage, empty past the end: wait_group counts stay uniform
   };
@@ -366,8 +394,8 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   // The ring is deep (up to 16 groups), so a refill is never urgent and nobody spins on done[].
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&done[s], (uint32_t)nwarps);
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(done0 + 8 * s, (uint32_t)nwarps);
     }
     mbar_fence_init();
   }
@@ -382,23 +410,26 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
       cellpart_t[(G0 + st) * (R * NQ) + lane] = s;
     }
   };
-  int i_next = warp, i_slot = warp % NS, i_k = warp / NS;  // issue cursor over this warp's stages: stage = i_k*NS + i_slot
-  int consumed = 0;                                        // stages this warp has finished
+  // issue cursor over this warp's stages: stage i_next = i_k*NS + i_slot; i_need = the stage that must have left
+  // the slot (i_next - NS), pushed out of reach once the warp has nothing more to issue
+  int i_next = warp, i_slot = warp % NS, i_k = warp / NS;
+  int consumed = 0;  // stages this warp has finished
+  int i_need = i_next < n_stages ? i_next - NS : 0x3fffffff;
+  const uint32_t tab_bytes = (uint32_t)TABG * 4u;
   auto issue_table = [&]() -> bool {  // warp-uniform; never blocks; true if a stage was issued
-    if (i_next >= n_stages) return false;
-    if (i_k > 0) {  // the slot held stage i_next - NS: wait until every warp has left it, then drain its partials
-      // A parity wait only distinguishes adjacent phases: do not look at done[] before this warp itself has
-      // arrived for stage i_next - NS (with fewer slots than warps its next stage is two phases ahead).
-      if (i_next - NS >= consumed) return false;
+    // A parity wait only distinguishes adjacent phases: do not look at done[] before this warp itself has
+    // arrived for stage i_need (with fewer slots than warps its next stage is two phases ahead).
+    if (i_need >= consumed) return false;
+    if (i_k > 0) {  // the slot held stage i_need: wait until every warp has left it, then drain its partials
       int ready = 0;
-      if (lane == 0) ready = mbar_test_wait(&done[i_slot], (uint32_t)((i_k - 1) & 1)) ? 1 : 0;
+      if (lane == 0) ready = mbar_test_wait(done0 + 8 * i_slot, (uint32_t)((i_k - 1) & 1)) ? 1 : 0;
       if (!__shfl_sync(0xffffffffu, ready, 0)) return false;
-      if (GRAD) flush_partials(i_next - NS, i_slot);
+      if (GRAD) flush_partials(i_need, i_slot);
       __syncwarp();
     }
     if (lane == 0) {
-      mbar_expect_tx(&full[i_slot], (uint32_t)TABG * 4u);
-      bulk_g2s(s_tab + (size_t)i_slot * TABG, P.tab + (G0 + i_next) * TABG, (uint32_t)TABG * 4u, &full[i_slot]);
+      mbar_expect_tx(full0 + 8 * i_slot, tab_bytes);
+      bulk_g2s(smem_u32(s_tab) + (uint32_t)i_slot * tab_bytes, P.tab + (G0 + i_next) * TABG, tab_bytes, full0 + 8 * i_slot);
     }
     i_next += nwarps;
     i_slot += nwarps;
@@ -406,21 +437,164 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
       i_slot -= NS;
       ++i_k;
     }
+    i_need = i_next < n_stages ? i_next - NS : 0x3fffffff;
     return true;
   };
   while (i_k == 0 && issue_table()) {}  // prologue: the slots are fresh
 #pragma unroll
-  for (int s = 0; s < D; ++s) load_counts(s, s);
+  for (int s = 0; s < D; ++s) load_counts(s);
 
   const float2 one2 = f2s(1.f), neg1 = f2s(-1.f), l2e = f2s(kLog2e), eps2 = f2s(1e-5f);
-  int since_fold = 0;
   int c_slot = 0, c_phase = 0, c_d = 0;  // consumer cursor: table slot / parity, count depth slot
+  const float4* const s_cnt = reinterpret_cast<const float4*>(smem_raw + L.cnt_off) + tid;  // this lane's column
+
+  // One 8-cell group.  MIXED (compile-time copy of the loop body): the group's cells belong to different batches
+  // (unsorted input), so batch offsets are added per element and d/ddnu goes through atomics -- rare and slow.
+  auto process = [&](auto mixed_tag, const int st, const float* tb, const float4* cnt, float (&pcf)[2], float (&pphi)[2],
+                     float (&pom)[2]) {
+    constexpr bool MIXED = decltype(mixed_tag)::value;
+    const float4* tb4 = reinterpret_cast<const float4*>(tb);
+    int bc[2] = {0, 0};
+    if (MIXED) {
+      bc[0] = __float_as_int(tb[TAIL + 8 + q]);
+      bc[1] = __float_as_int(tb[TAIL + 12 + q]);
+    }
+    float om[2] = {0.f, 0.f};
+    if (VELO) {
+      om[0] = tb[TAIL + q];
+      om[1] = tb[TAIL + q + 4];
+    }
+    float2 pcf2[2] = {zero2, zero2}, pphi2[2] = {zero2, zero2}, pom2[2] = {zero2, zero2};
+    const float2* cnt2 = reinterpret_cast<const float2*>(cnt);
+
+    // one row tile (16 genes x 8 cells) at a time: forward MMAs -> element terms -> backward MMAs, so that only one
+    // tile's accumulator fragments are live
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+      const int p = mt >> 1, t = mt & 1;
+      // ---- forward contractions on the tensor pipe -----------------------------------------------------
+      float Ce[4] = {0.f, 0.f, 0.f, 0.f}, Cd[4] = {0.f, 0.f, 0.f, 0.f}, Cw[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        mma_split(Ce, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F0 * KS + ks) * 32 + lane]);
+        if (NEED_D) mma_split(Cd, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F1 * KS + ks) * 32 + lane]);
+        if (NEED_E) mma_split(Cw, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F2 * KS + ks) * 32 + lane]);
+      }
+      const float4 ga = s_gene[(mt * 2 + 0) * 8];
+      const float2 nr_mt = f2(ga.x, ga.y);
+      float2 gam_mt = one2, invb_mt = one2;
+      if (VELO) {
+        const float4 gb = s_gene[(mt * 2 + 1) * 8];
+        gam_mt = f2(gb.x, gb.y);
+        invb_mt = f2(gb.z, gb.w);
+      }
+
+      // ---- per-element negative-binomial terms (gene pair x cells q, q+4) ------------------------------------
+      float2 Gg[2], Gw[2];  // backward A operands of this row tile
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        // this lane's slot j holds its 4 genes of pair p: .xy row tile 2p, .zw row tile 2p+1
+        const float2 kS = cnt2[((size_t)(cc * NPAIR + p) * nthr) * 2 + t];
+        const float2 kU = VELO ? cnt2[((size_t)((2 + cc) * NPAIR + p) * nthr) * 2 + t] : kS;
+        float2 c0 = f2(ga.z, ga.w);
+        if (MIXED) {  // the table's constant term carries the offset of cur_b: use the cell's own batch instead
+          const long long g0 = gene_of(mt, 0);
+          c0 = f2(const_term(g0, bc[cc]), const_term(g0 + 1, bc[cc]));
+        }
+        const float2 eta = add2(f2(Ce[cc], Ce[2 + cc]), c0);
+        const float2 d = f2(Cd[cc], Cd[2 + cc]);
+        const float2 y = mul2(eta, l2e);
+        const float2 u = ex2_2(y);
+        const float2 s = add2(u, one2);
+        const float2 LS = lg2_2(s);
+        accAS[mt] = fma2(kS, fma2(LS, neg1, y), accAS[mt]);
+        accLS[mt] = add2(accLS[mt], LS);
+        if (LGINLINE) {
+          float2 psi, lg;
+          lg.x = lgamma_terms_inline(-nr_mt.x, kS.x, psi.x);
+          lg.y = lgamma_terms_inline(-nr_mt.y, kS.y, psi.y);
+          accAS[mt] = fma2(lg, l2e, accAS[mt]);
+          accPsi[mt] = add2(accPsi[mt], psi);
+        }
+        float2 g = zero2, w = zero2;
+        if (VELO) {
+          const float2 a = fma2(d, f2s(om[cc]), gam_mt);
+          const float2 m = add2(f2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), eps2);
+          const float2 mb = mul2(m, invb_mt);
+          const float2 uU = mul2(u, mb);
+          const float2 sU = add2(uU, one2);
+          const float2 LU = lg2_2(sU);
+          const float2 lmb = lg2_2(mb);
+          accAU[mt] = fma2(kU, fma2(LU, neg1, add2(y, lmb)), accAU[mt]);
+          accLU[mt] = add2(accLU[mt], LU);
+          if (LGINLINE) {
+            float2 psi, lg;
+            lg.x = lgamma_terms_inline(-nr_mt.x, kU.x, psi.x);
+            lg.y = lgamma_terms_inline(-nr_mt.y, kU.y, psi.y);
+            accAU[mt] = fma2(lg, l2e, accAU[mt]);
+            accPsi[mt] = add2(accPsi[mt], psi);
+          }
+          if (GRAD) {
+            const float2 sUm = mul2(sU, m);
+            const float2 rc = rcp_2(mul2(s, sUm));  // one MUFU for 1/s and 1/(sU m)
+            const float2 inv_s = mul2(rc, sUm), inv_sUm = mul2(rc, s);
+            const float2 gS = mul2(fma2(nr_mt, u, kS), inv_s);
+            const float2 w0 = mul2(fma2(nr_mt, uU, kU), inv_sUm);
+            const float2 gU = mul2(w0, m);
+            w = f2(a.x > 0.f ? w0.x : 0.f, a.y > 0.f ? w0.y : 0.f);
+            g = add2(gS, gU);
+            accGU[mt] = add2(accGU[mt], gU);
+            pom2[cc] = fma2(w, d, pom2[cc]);
+            pphi2[cc] = fma2(w, f2(Cw[cc], Cw[2 + cc]), pphi2[cc]);
+          }
+        } else if (GRAD) {
+          g = mul2(fma2(nr_mt, u, kS), rcp_2(s));
+        }
+        if (GRAD) {
+          pcf2[cc] = add2(pcf2[cc], g);
+          pphi2[cc] = fma2(g, d, pphi2[cc]);
+          if (MIXED) {
+            if ((G0 + st) * R + q + 4 * cc < P.Nc) {
+              const long long g0 = gene_of(mt, 0), brow = (long long)bc[cc] * P.Ng;
+              if (g0 < P.Ng) atomicAdd(&P.d_dnu[brow + g0], g.x);
+              if (g0 + 1 < P.Ng) atomicAdd(&P.d_dnu[brow + g0 + 1], g.y);
+            }
+          }
+        }
+        Gg[cc] = g;
+        Gw[cc] = w;
+      }
+
+      // ---- backward contractions on the tensor pipe: acc[gene][slot] = sum_cells G[gene][cell] Z[cell][slot] -----
+      if (GRAD) {
+        uint32_t gm[4], gx[4], wm[4], wx[4];
+        split_operand(Gg[0], Gg[1], gm, gx);
+        if (VELO) split_operand(Gw[0], Gw[1], wm, wx);
+#pragma unroll
+        for (int nt = 0; nt < KS; ++nt) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          float4 bz = tb4[(SEC_B0 * KS + nt) * 32 + lane];
+          if (MIXED && nt == 0 && grp == 0) bz.x = bz.y = bz.z = 0.f;  // constant column off: d/ddnu went through atomics
+          mma_split(acc, gm, gx, bz);
+          if (VELO) mma_split(acc, wm, wx, tb4[(SEC_B1 * KS + nt) * 32 + lane]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) accNu[mt][nt][i] += acc[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      pcf[cc] = pcf2[cc].x + pcf2[cc].y;
+      pphi[cc] = pphi2[cc].x + pphi2[cc].y;
+      pom[cc] = pom2[cc].x + pom2[cc].y;
+    }
+  };
 
   // ---- main loop ----------------------------------------------------------------------------------
   for (int st = 0; st < n_stages; ++st) {
     {
       uint32_t spins = 0;
-      while (!__all_sync(0xffffffffu, mbar_try_wait(&full[c_slot], (uint32_t)c_phase))) {
+      while (!__all_sync(0xffffffffu, mbar_try_wait(full0 + 8 * c_slot, (uint32_t)c_phase))) {
         issue_table();
         if (++spins > (1u << 24)) __trap();
       }
@@ -429,163 +603,24 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     __syncwarp();            // ... and so have the other lanes' (counts never cross a warp)
     const float* tb = s_tab + (size_t)c_slot * TABG;
     const float4* cnt = s_cnt + (size_t)c_d * NLD * nthr;
-    const float4* tb4 = reinterpret_cast<const float4*>(tb);
     float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
 
     if (!P.debug_skip_compute) {
-      // ---- batch bookkeeping (CTA-uniform decisions: every warp reads the same table) -----------------
+      // batch bookkeeping (CTA-uniform decisions: every warp reads the same table)
       bool mixed = false;
-      int bc[2] = {0, 0};
       if (P.Nb > 0) {
-        const int4 b0 = *reinterpret_cast<const int4*>(tb + TAIL + 8);
-        const int4 b1 = *reinterpret_cast<const int4*>(tb + TAIL + 12);
-        mixed = !(b0.x == b0.y && b0.x == b0.z && b0.x == b0.w && b0.x == b1.x && b0.x == b1.y && b0.x == b1.z &&
-                  b0.x == b1.w);
-        if (!mixed && b0.x != cur_b) {
+        const int gb = __float_as_int(tb[TAIL + 16]);  // the group's batch, -1 if its cells disagree
+        mixed = gb < 0;
+        if (!mixed && gb != cur_b) {
           if (GRAD) flush_batch();
-          cur_b = b0.x;
+          cur_b = gb;
           set_batch(cur_b);
         }
-        if (mixed) {  // rare (unsorted batches): offsets are added per element, d/ddnu goes through atomics
-          bc[0] = __float_as_int(tb[TAIL + 8 + q]);
-          bc[1] = __float_as_int(tb[TAIL + 12 + q]);
-        }
       }
-
-      // ---- forward contractions on the tensor pipe -------------------------------------------------------
-      float Ce[NT][4], Cd[NT][4], Cw[NT][4];
-#pragma unroll
-      for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) Ce[mt][i] = Cd[mt][i] = Cw[mt][i] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const float4 bz = tb4[(SEC_F0 * KS + ks) * 32 + lane];
-#pragma unroll
-        for (int mt = 0; mt < NT; ++mt) mma_split(Ce[mt], Amain[mt][ks], Across[mt][ks], bz);
-        if (NEED_D) {
-          const float4 bz1 = tb4[(SEC_F1 * KS + ks) * 32 + lane];
-#pragma unroll
-          for (int mt = 0; mt < NT; ++mt) mma_split(Cd[mt], Amain[mt][ks], Across[mt][ks], bz1);
-        }
-        if (NEED_E) {
-          const float4 bz2 = tb4[(SEC_F2 * KS + ks) * 32 + lane];
-#pragma unroll
-          for (int mt = 0; mt < NT; ++mt) mma_split(Cw[mt], Amain[mt][ks], Across[mt][ks], bz2);
-        }
-      }
-      float om[2] = {0.f, 0.f};
-      if (VELO) {
-        om[0] = tb[TAIL + q];
-        om[1] = tb[TAIL + q + 4];
-      }
-
-      // ---- per-element negative-binomial terms ---------------------------------------------------------------
-      float2 Gg[NT][2], Gw[NT][2];  // backward A operands: [row tile][cell q / q+4] = gene pair
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const float2 om2 = f2s(om[cc]);
-        float2 pcf2 = zero2, pphi2 = zero2, pom2 = zero2;
-#pragma unroll
-        for (int p = 0; p < NPAIR; ++p) {
-          const float4 s4 = cnt[(size_t)(cc * NPAIR + p) * nthr];
-          const float4 u4 = VELO ? cnt[(size_t)((2 + cc) * NPAIR + p) * nthr] : s4;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int mt = 2 * p + t;
-            const float2 kS = t ? f2(s4.z, s4.w) : f2(s4.x, s4.y);
-            const float2 kU = t ? f2(u4.z, u4.w) : f2(u4.x, u4.y);
-            float2 eta = add2(f2(Ce[mt][cc], Ce[mt][2 + cc]), nu0c[mt]);
-            const float2 d = f2(Cd[mt][cc], Cd[mt][2 + cc]);
-            if (mixed) {  // nu0c carries the offset of cur_b: swap it for the cell's own batch
-              const long long g0 = gene_of(mt, 0);
-              eta = add2(f2(Ce[mt][cc], Ce[mt][2 + cc]), f2(const_term(g0, bc[cc]), const_term(g0 + 1, bc[cc])));
-            }
-            const float2 y = mul2(eta, l2e);
-            const float2 u = ex2_2(y);
-            const float2 s = add2(u, one2);
-            const float2 LS = lg2_2(s);
-            accAS[mt] = fma2(kS, fma2(LS, neg1, y), accAS[mt]);
-            accLS[mt] = add2(accLS[mt], LS);
-            if (LGINLINE) {
-              float2 psi, lg;
-              lg.x = lgamma_terms_inline(-nr[mt].x, kS.x, psi.x);
-              lg.y = lgamma_terms_inline(-nr[mt].y, kS.y, psi.y);
-              accAS[mt] = fma2(lg, l2e, accAS[mt]);
-              accPsi[mt] = add2(accPsi[mt], psi);
-            }
-            float2 g = zero2, w = zero2;
-            if (VELO) {
-              const float2 a = fma2(d, om2, gam[mt]);
-              const float2 m = add2(f2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), eps2);
-              const float2 mb = mul2(m, invb[mt]);
-              const float2 uU = mul2(u, mb);
-              const float2 sU = add2(uU, one2);
-              const float2 LU = lg2_2(sU);
-              const float2 lmb = lg2_2(mb);
-              accAU[mt] = fma2(kU, fma2(LU, neg1, add2(y, lmb)), accAU[mt]);
-              accLU[mt] = add2(accLU[mt], LU);
-              if (LGINLINE) {
-                float2 psi, lg;
-                lg.x = lgamma_terms_inline(-nr[mt].x, kU.x, psi.x);
-                lg.y = lgamma_terms_inline(-nr[mt].y, kU.y, psi.y);
-                accAU[mt] = fma2(lg, l2e, accAU[mt]);
-                accPsi[mt] = add2(accPsi[mt], psi);
-              }
-              if (GRAD) {
-                const float2 sUm = mul2(sU, m);
-                const float2 rc = rcp_2(mul2(s, sUm));  // one MUFU for 1/s and 1/(sU m)
-                const float2 inv_s = mul2(rc, sUm), inv_sUm = mul2(rc, s);
-                const float2 gS = mul2(fma2(nr[mt], u, kS), inv_s);
-                const float2 w0 = mul2(fma2(nr[mt], uU, kU), inv_sUm);
-                const float2 gU = mul2(w0, m);
-                w = f2(a.x > 0.f ? w0.x : 0.f, a.y > 0.f ? w0.y : 0.f);
-                g = add2(gS, gU);
-                accGU[mt] = add2(accGU[mt], gU);
-                pom2 = fma2(w, d, pom2);
-                pphi2 = fma2(w, f2(Cw[mt][cc], Cw[mt][2 + cc]), pphi2);
-              }
-            } else if (GRAD) {
-              g = mul2(fma2(nr[mt], u, kS), rcp_2(s));
-            }
-            if (GRAD) {
-              pcf2 = add2(pcf2, g);
-              pphi2 = fma2(g, d, pphi2);
-              if (mixed && (G0 + st) * R + q + 4 * cc < P.Nc) {
-                const long long g0 = gene_of(mt, 0), brow = (long long)bc[cc] * P.Ng;
-                if (g0 < P.Ng) atomicAdd(&P.d_dnu[brow + g0], g.x);
-                if (g0 + 1 < P.Ng) atomicAdd(&P.d_dnu[brow + g0 + 1], g.y);
-              }
-            }
-            Gg[mt][cc] = g;
-            Gw[mt][cc] = w;
-          }
-        }
-        pcf[cc] = pcf2.x + pcf2.y;
-        pphi[cc] = pphi2.x + pphi2.y;
-        pom[cc] = pom2.x + pom2.y;
-      }
-
-      // ---- backward contractions on the tensor pipe: accT[gene][slot] += sum_cells G[gene][cell] Z[cell][slot] --
-      if (GRAD) {
-#pragma unroll
-        for (int mt = 0; mt < NT; ++mt) {
-          uint32_t gm[4], gx[4], wm[4], wx[4];
-          split_operand(Gg[mt][0], Gg[mt][1], gm, gx);
-          if (VELO) split_operand(Gw[mt][0], Gw[mt][1], wm, wx);
-#pragma unroll
-          for (int nt = 0; nt < KS; ++nt) {
-            float4 bz = tb4[(SEC_B0 * KS + nt) * 32 + lane];
-            if (mixed && nt == 0 && grp == 0) bz.x = bz.y = bz.z = 0.f;  // constant column off: d/ddnu went through atomics
-            mma_split(accT[mt][nt], gm, gx, bz);
-            if (VELO) mma_split(accT[mt][nt], wm, wx, tb4[(SEC_B1 * KS + nt) * 32 + lane]);
-          }
-        }
-        if (++since_fold == kFlushEvery) {
-          fold_acc();
-          since_fold = 0;
-        }
-      }
+      if (mixed)
+        process(BoolTag<true>{}, st, tb, cnt, pcf, pphi, pom);
+      else
+        process(BoolTag<false>{}, st, tb, cnt, pcf, pphi, pom);
     }
 
     if (GRAD) {
@@ -608,13 +643,13 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&done[c_slot]);  // this warp no longer needs the slot (release: partials are visible)
+    if (lane == 0) mbar_arrive(done0 + 8 * c_slot);  // this warp no longer needs the slot (release: partials are visible)
     if (++c_slot == NS) {
       c_slot = 0;
       c_phase ^= 1;
     }
     consumed = st + 1;
-    load_counts(st + D, c_d);  // refill the count slot this thread has just consumed
+    load_counts(c_d);  // refill the count slot this warp has just consumed
     if (++c_d == D) c_d = 0;
     issue_table();
   }
@@ -628,13 +663,7 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   }
 
   // ---- flush per-gene partial sums ----------------------------------------------------------------
-  if (GRAD) {
-    if (P.Nb > 0) {
-      flush_batch();
-    } else {
-      fold_acc();
-    }
-  }
+  if (GRAD && P.Nb > 0) flush_batch();
   constexpr int ROWS = gene_rows(H);
   float* gp = P.genepart + ((long long)split * ROWS) * P.ld;
   auto lane_sum4 = [&](float2 v) -> float2 {  // over the 4 lanes (cells) that share a gene pair
