@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
       v[2][lane][kc] = omega * (-fn * fn * co);
     }
     // spare slot K: the size factor rides the forward contraction (A holds 1 there); a padding cell gets
-    // eta = -inf so that all its terms vanish; backward it collects sum_c w = d/dgamma
-    v[0][lane][K] = valid ? (P.cf ? P.cf[c] : 0.f) : -1e30f;
+    // eta = -3e4 so that all its terms vanish; backward it collects sum_c w = d/dgamma
+    v[0][lane][K] = valid ? (P.cf ? P.cf[c] : 0.f) : -30000.f;  // (inside the FP16 range of the cross-term operand)
     v[4][lane][K] = 1.f;
     s_tail[warp][lane] = omega;
     s_tail[warp][8 + lane] = __int_as_float(P.batch_id ? P.batch_id[cl] : 0);
@@ -93,11 +93,13 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
   __syncwarp();
   const int grp = lane >> 2, q = lane & 3;
   float4* out = reinterpret_cast<float4*>(P.tab + group * P.tabg);
-  // one table entry: {TF32 hi of the main MMA's b0, b1; BF16x2 {y0, y1} and {lo y0, lo y1} of the cross-term MMA}
-  auto emit = [&](int sec_out, int ks, float x0, float x1, float y0, float y1) {
-    out[(sec_out * KS + ks) * 32 + lane] =
-        make_float4(__uint_as_float(tf32_rna(x0)), __uint_as_float(tf32_rna(x1)), __uint_as_float(pack_bf16(y0, y1)),
-                    __uint_as_float(pack_bf16(tf32_lo(y0), tf32_lo(y1))));
+  // one table entry: {TF32 hi of the main MMA's b0, b1; 16-bit pairs {y0, y1} and {lo y0, lo y1} of the cross-term
+  // MMA: FP16 for the forward sections, BF16 for the backward ones (see mma_split_fwd / mma_split_bwd)}
+  auto emit = [&](int sec_out, int ks, bool f16, float x0, float x1, float y0, float y1) {
+    const uint32_t c0 = f16 ? pack_f16(y0, y1) : pack_bf16(y0, y1);
+    const uint32_t c1 = f16 ? pack_f16(tf32_lo(y0), tf32_lo(y1)) : pack_bf16(tf32_lo(y0), tf32_lo(y1));
+    out[(sec_out * KS + ks) * 32 + lane] = make_float4(__uint_as_float(tf32_rna(x0)), __uint_as_float(tf32_rna(x1)),
+                                                       __uint_as_float(c0), __uint_as_float(c1));
   };
   const int fc = fwd_cell(grp);
   for (int ks = 0; ks < KS; ++ks) {
@@ -105,12 +107,12 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
     // column n is cell fwd_cell(n)
     auto fwd = [&](int sec_out, int sec) {
       const float* z = sv[warp][sec][fc] + 8 * ks;
-      emit(sec_out, ks, z[q], z[q + 4], z[2 * q], z[2 * q + 1]);
+      emit(sec_out, ks, true, z[q], z[q + 4], z[2 * q], z[2 * q + 1]);
     };
     // backward: k runs over cells: main b0 (cell q, n = slot grp), b1 (cell q+4); cross pairs the same two cells
     auto bwd = [&](int sec_out, int sec) {
       const float z0 = sv[warp][sec][q][8 * ks + grp], z1 = sv[warp][sec][q + 4][8 * ks + grp];
-      emit(sec_out, ks, z0, z1, z0, z1);
+      emit(sec_out, ks, false, z0, z1, z0, z1);
     };
     fwd(SEC_F0, 0);
     fwd(SEC_F1, 1);

@@ -6,8 +6,8 @@
 // 61 fp32 operations of the element.  The fp32 pipe, not HBM, bounded the first version of this kernel
 // (DESIGN.md section 4), so those contractions now run on the tensor pipe as warp-level m16n8k8 TF32 MMAs
 // with the split x = hi + lo that keeps fp32-level accuracy: A.B ~ Ahi.Bhi (one m16n8k8 TF32 MMA, SASS
-// HMMA.1688.F32.TF32) + [Alo | A].[B ; Blo] (both cross terms in ONE m16n8k16 BF16 MMA, HMMA.16816.F32.BF16:
-// they are 2^-11 of the product, so 8 mantissa bits suffice); lo*lo is dropped.  The fp32 pipe keeps the
+// HMMA.1688.F32.TF32) + [Alo | A].[B ; Blo] (both cross terms in ONE m16n8k16 FP16 / BF16 MMA, HMMA.16816.F32:
+// they are 2^-11 of the product, so 8-11 mantissa bits suffice); lo*lo is dropped.  The fp32 pipe keeps the
 // negative-binomial terms, the MUFU pipe the 5 transcendentals.  The harmonics 1..2H (<= 6) fit one 8-wide
 // k-step together with one spare slot that carries the per-cell size factor forward and sum_c w (= d/dgamma)
 // backward; the constant term nu_0 - ln r (+ batch offset) is added in fp32 (it is the largest addend).  (tcgen05 is the wrong tool here: its operands live in shared memory, and
@@ -141,6 +141,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float k_even, float k_odd) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(k_odd), "f"(k_even));
   return r;
 }
+// same for FP16 (3 more mantissa bits than BF16; used where the operands are bounded: nu and the basis tables);
+// values beyond the FP16 range saturate instead of turning into infinities
+__device__ __forceinline__ uint32_t pack_f16(float k_even, float k_odd) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(k_odd), "f"(k_even));
+  return r;
+}
 // Fragments (grp = lane/4, q = lane%4).  m16n8k8 TF32:
 //   a0 (grp, q)  a1 (grp+8, q)  a2 (grp, q+4)  a3 (grp+8, q+4);  b0 (k=q, n=grp)  b1 (k=q+4, n=grp);
 //   c0 (grp, 2q)  c1 (grp, 2q+1)  c2 (grp+8, 2q)  c3 (grp+8, 2q+1)
@@ -159,10 +166,23 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// C += A.B with A = amain (TF32 hi) and the cross terms folded into across = [Alo | A] (BF16), small terms first;
-// b = one table entry {main b0, main b1, cross b0, cross b1}
-__device__ __forceinline__ void mma_split(float (&c)[4], const uint32_t (&amain)[4], const uint32_t (&across)[4],
-                                          const float4 b) {
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// C += A.B with A = amain (TF32 hi) and the cross terms folded into across = [Alo | A], small terms first;
+// b = one table entry {main b0, main b1, cross b0, cross b1}.  Forward (nu x basis tables, bounded operands) the
+// cross operands are FP16: error 2^-11 * 2^-12 of the product, i.e. fp32 level.  Backward (the A operand is a
+// per-element gradient of unbounded range) they are BF16: 2^-20 per element, random over the cells of a sum.
+__device__ __forceinline__ void mma_split_fwd(float (&c)[4], const uint32_t (&amain)[4], const uint32_t (&across)[4],
+                                              const float4 b) {
+  mma_f16(c, across, __float_as_uint(b.z), __float_as_uint(b.w));
+  mma_tf32(c, amain, __float_as_uint(b.x), __float_as_uint(b.y));
+}
+__device__ __forceinline__ void mma_split_bwd(float (&c)[4], const uint32_t (&amain)[4], const uint32_t (&across)[4],
+                                              const float4 b) {
   mma_bf16(c, across, __float_as_uint(b.z), __float_as_uint(b.w));
   mma_tf32(c, amain, __float_as_uint(b.x), __float_as_uint(b.y));
 }
@@ -261,8 +281,8 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
         const float x0 = a_value(gene_of(mt, o), 8 * ks + 2 * q), x1 = a_value(gene_of(mt, o), 8 * ks + 2 * q + 1);
-        Across[mt][ks][o] = pack_bf16(tf32_lo(x0), tf32_lo(x1));
-        Across[mt][ks][2 + o] = pack_bf16(x0, x1);
+        Across[mt][ks][o] = pack_f16(tf32_lo(x0), tf32_lo(x1));
+        Across[mt][ks][2 + o] = pack_f16(x0, x1);
       }
     }
     if (q == 0) {
@@ -476,9 +496,9 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
       float Ce[4] = {0.f, 0.f, 0.f, 0.f}, Cd[4] = {0.f, 0.f, 0.f, 0.f}, Cw[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        mma_split(Ce, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F0 * KS + ks) * 32 + lane]);
-        if (NEED_D) mma_split(Cd, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F1 * KS + ks) * 32 + lane]);
-        if (NEED_E) mma_split(Cw, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F2 * KS + ks) * 32 + lane]);
+        mma_split_fwd(Ce, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F0 * KS + ks) * 32 + lane]);
+        if (NEED_D) mma_split_fwd(Cd, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F1 * KS + ks) * 32 + lane]);
+        if (NEED_E) mma_split_fwd(Cw, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F2 * KS + ks) * 32 + lane]);
       }
       const float4 ga = s_gene[(mt * 2 + 0) * 8];
       const float2 nr_mt = f2(ga.x, ga.y);
@@ -575,8 +595,8 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
           float4 bz = tb4[(SEC_B0 * KS + nt) * 32 + lane];
           if (MIXED && nt == 0 && grp == 0) bz.x = bz.y = bz.z = 0.f;  // constant column off: d/ddnu went through atomics
-          mma_split(acc, gm, gx, bz);
-          if (VELO) mma_split(acc, wm, wx, tb4[(SEC_B1 * KS + nt) * 32 + lane]);
+          mma_split_bwd(acc, gm, gx, bz);
+          if (VELO) mma_split_bwd(acc, wm, wx, tb4[(SEC_B1 * KS + nt) * 32 + lane]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) accNu[mt][nt][i] += acc[i];
         }
