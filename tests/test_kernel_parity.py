@@ -112,6 +112,77 @@ def test_fused_matches_oracle(shape, velocity):
     assert n >= (9 if velocity else 6)
 
 
+# Shapes whose CTAs walk many more 8-cell groups than either shared-memory ring holds (count ring: 6 groups; table
+# ring: 6-16 groups, FEWER slots than warps for the velocity model -> the two-phases-ahead case of the mbarrier
+# parity waits), with batch boundaries inside CTAs and a ragged last group.
+RING_SHAPES = [
+    # Nc, Ng, H, Hw, Nb, Nx, sorted
+    (20003, 2000, 3, 1, 1, 1, True),    # BASELINE gene count: 4 gene tiles x 37 cell splits, ~68 groups per CTA
+    (30001, 512, 1, 1, 3, 2, True),     # one gene tile, 148 cell splits, batch boundaries inside CTAs
+    (9000, 40, 2, 1, 4, 2, False),      # 2-warp CTAs (8 per SM), every group mixes batches
+]
+
+
+@pytest.mark.parametrize("shape", RING_SHAPES)
+@pytest.mark.parametrize("velocity", [False, True])
+def test_long_streams_match_oracle(shape, velocity):
+    from velocycle_b200.synthetic import make_synthetic
+
+    Nc, Ng, H, Hw, Nb, Nx, sorted_b = shape
+    d = make_synthetic(Nc, Ng, H=H, Hw=Hw, Nb=Nb, Nx=Nx, seed=13, device="cuda", sorted_batches=sorted_b)
+    out, ref, _ = _run(d, velocity)
+    _compare(out, ref)
+
+
+def test_results_are_deterministic():
+    """No atomics on the hot path (sorted batches): two evaluations agree bit for bit."""
+    from velocycle_b200.fused import PackedCounts, fused_elbo_grad
+    from velocycle_b200.synthetic import make_synthetic
+
+    d = make_synthetic(20000, 700, H=3, Hw=1, Nb=1, Nx=2, seed=5, device="cuda")
+    counts = PackedCounts(d.S, d.U, d.Ng, d.batch_id, d.cond_id)
+    args = (counts, d.phi, d.cf, d.nu, None, d.shape_inv, d.logbeta, torch.exp(d.loggamma), d.nu_omega)
+    a = {k: v.clone() for k, v in fused_elbo_grad(*args, grad=True).items()}
+    b = fused_elbo_grad(*args, grad=True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_full_size_properties():
+    """BASELINE's 1M x 2k is far beyond what the CPU oracle evaluates in seconds; check size-independent properties:
+    (i) additivity over cells: per-gene sums of the whole matrix = sum over two row blocks evaluated separately
+    (every per-gene output is a plain sum over cells), (ii) per-cell outputs do not depend on the other cells."""
+    from velocycle_b200.fused import PackedCounts, fused_elbo_grad
+    from velocycle_b200.synthetic import make_synthetic
+
+    Nc, cut = 200_000, 77_777  # (kept below 1M so that the test box needs ~5 GB; the code path is size-agnostic)
+    d = make_synthetic(Nc, 2000, H=3, Hw=1, Nb=1, Nx=1, seed=17, device="cuda", stats=False)
+    d.shape_inv = d.shape_inv * 2.0  # away from the optimum: d/dshape_inv is then not pure cancellation noise
+    d.nu = d.nu + 0.2 * torch.randn(d.nu.shape, generator=torch.Generator().manual_seed(1)).to(d.nu.device)
+    gamma = torch.exp(d.loggamma)
+
+    def run(lo, hi):
+        c = PackedCounts(d.S[lo:hi], d.U[lo:hi], d.Ng, d.batch_id[lo:hi], d.cond_id[lo:hi])
+        return fused_elbo_grad(c, d.phi[lo:hi], d.cf[lo:hi], d.nu, None, d.shape_inv, d.logbeta, gamma, d.nu_omega,
+                               grad=True)
+
+    whole, a, b = run(0, Nc), run(0, cut), run(cut, Nc)
+    for k in ("d_nu", "d_logbeta", "d_gamma", "d_nu_omega"):
+        want = a[k].double() + b[k].double()
+        err = float((whole[k].double() - want).abs().max() / want.abs().max())
+        assert err <= 1e-5, (k, err)
+    # these also carry the count-spectrum terms, additive over cells as well; d/dshape_inv is a difference of
+    # sums ~1e3 times larger than itself (psi - L - dnu0/r), so fp32 partial sums leave it ~1e-3 accurate
+    for k, tol in (("lp_S", 1e-5), ("lp_U", 1e-5), ("d_shape_inv", 2e-3)):
+        want = a[k].double() + b[k].double()
+        err = float((whole[k].double() - want).abs().max() / want.abs().max())
+        assert err <= tol, (k, err)
+    for k in ("d_phi", "d_cf"):
+        want = torch.cat([a[k], b[k]]).double()
+        err = float((whole[k].double() - want).abs().max() / want.abs().max())
+        assert err <= 1e-5, (k, err)
+
+
 @pytest.mark.parametrize("velocity", [False, True])
 def test_inline_lgamma_matches_oracle(velocity):
     from velocycle_b200.synthetic import make_synthetic

@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Potentially-suspending probe; the suspend time is capped at ~0.2 us because the waiting warps also have
+// Potentially-suspending probe; the suspend time is capped at ~1 us because the waiting warps also have
 // refill duties that depend on OTHER barriers (a long park would delay them).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -57,7 +57,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(200u)
+      : "r"(bar), "r"(parity), "r"(1000u)
       : "memory");
   return ok != 0;
 }

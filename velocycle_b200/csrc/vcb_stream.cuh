@@ -45,7 +45,7 @@
 namespace vcb {
 
 constexpr int kGroupCells = 8;  // cells per ring stage = the n extent (forward) / k extent (backward) of the MMAs
-constexpr int kCountDepth = 6;  // count groups in flight per thread (6 x 32 KB per 512-thread CTA)
+constexpr int kCountDepth = 5;  // count groups in flight per thread (5 x 32 KB per 512-thread CTA)
 constexpr int kMaxStages = 16;  // the table ring is as deep as the rest of shared memory allows, up to this
 constexpr int kSmemHeader = 512;
 
@@ -88,7 +88,7 @@ struct StreamParams {
 };
 
 struct StreamSmem {
-  int part_off, gene_off, tab_off, cnt_off, total;  // byte offsets inside dynamic shared memory
+  int part_off, gene_off, aop_off, tab_off, cnt_off, total;  // byte offsets inside dynamic shared memory
 };
 
 __host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, int nwarps, int npair, int n_ring) {
@@ -99,6 +99,8 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, int n
   off = (off + 127) / 128 * 128;
   L.gene_off = off;  // per-gene parameters: [warp][row tile][2][grp] float4
   off += nwarps * 2 * npair * 2 * 8 * 16;
+  L.aop_off = off;  // forward A operands (nu fragments): [warp][row tile][k-step][main / cross][lane] uint4
+  off += nwarps * 2 * npair * ksteps(H) * 2 * 32 * 16;
   L.tab_off = off;
   off += n_ring * table_group_floats(H, velo) * 4;
   off = (off + 127) / 128 * 128;
@@ -268,7 +270,10 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     if (b >= 0) v += P.dnu[(long long)b * P.Ng + g];
     return v;
   };
-  uint32_t Amain[NT][KS][4], Across[NT][KS][4];
+  // The nu fragments of the forward MMAs (TF32 hi for the main product, FP16 [lo | value] for the cross terms)
+  // are this lane's own, but 16 registers is more than the loop can spare: they wait in shared memory and come back
+  // with two LDS.128 per row tile and group.
+  uint4* const s_aop = reinterpret_cast<uint4*>(smem_raw + L.aop_off) + (size_t)warp * (NT * KS * 2 * 32) + lane;
   // Dispersion, kinetics and the constant term live in shared memory (the 4 lanes of a grp share them; one
   // broadcast LDS.128 per row tile brings {-r, c0} and {gamma, 1/beta} as gene pairs): 16 registers fewer.
   float4* const s_gene = reinterpret_cast<float4*>(smem_raw + L.gene_off) + (size_t)warp * (NT * 2 * 8) + grp;
@@ -276,14 +281,17 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   for (int mt = 0; mt < NT; ++mt) {
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
+      uint32_t am[4], ax[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) Amain[mt][ks][i] = tf32_rna(a_value(gene_of(mt, i & 1), 8 * ks + q + 4 * (i >> 1)));
+      for (int i = 0; i < 4; ++i) am[i] = tf32_rna(a_value(gene_of(mt, i & 1), 8 * ks + q + 4 * (i >> 1)));
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
         const float x0 = a_value(gene_of(mt, o), 8 * ks + 2 * q), x1 = a_value(gene_of(mt, o), 8 * ks + 2 * q + 1);
-        Across[mt][ks][o] = pack_f16(tf32_lo(x0), tf32_lo(x1));
-        Across[mt][ks][2 + o] = pack_f16(x0, x1);
+        ax[o] = pack_f16(tf32_lo(x0), tf32_lo(x1));
+        ax[2 + o] = pack_f16(x0, x1);
       }
+      s_aop[((mt * KS + ks) * 2 + 0) * 32] = make_uint4(am[0], am[1], am[2], am[3]);
+      s_aop[((mt * KS + ks) * 2 + 1) * 32] = make_uint4(ax[0], ax[1], ax[2], ax[3]);
     }
     if (q == 0) {
       float rs[2], gs[2], ibs[2];
@@ -496,9 +504,11 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
       float Ce[4] = {0.f, 0.f, 0.f, 0.f}, Cd[4] = {0.f, 0.f, 0.f, 0.f}, Cw[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        mma_split_fwd(Ce, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F0 * KS + ks) * 32 + lane]);
-        if (NEED_D) mma_split_fwd(Cd, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F1 * KS + ks) * 32 + lane]);
-        if (NEED_E) mma_split_fwd(Cw, Amain[mt][ks], Across[mt][ks], tb4[(SEC_F2 * KS + ks) * 32 + lane]);
+        const uint4 a0 = s_aop[((mt * KS + ks) * 2 + 0) * 32], a1 = s_aop[((mt * KS + ks) * 2 + 1) * 32];
+        const uint32_t am[4] = {a0.x, a0.y, a0.z, a0.w}, ax[4] = {a1.x, a1.y, a1.z, a1.w};
+        mma_split_fwd(Ce, am, ax, tb4[(SEC_F0 * KS + ks) * 32 + lane]);
+        if (NEED_D) mma_split_fwd(Cd, am, ax, tb4[(SEC_F1 * KS + ks) * 32 + lane]);
+        if (NEED_E) mma_split_fwd(Cw, am, ax, tb4[(SEC_F2 * KS + ks) * 32 + lane]);
       }
       const float4 ga = s_gene[(mt * 2 + 0) * 8];
       const float2 nr_mt = f2(ga.x, ga.y);
