@@ -320,7 +320,7 @@ def run_ours(a):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel": "vcb_stream_kernel", "kernel_ms": kern, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                "note": "fp32-pipe bound, not HBM bound (see DESIGN.md section 4 and profiles/)"}
+                "note": "latency / issue-slot bound at 16 warps per SM, not HBM bound: every pipe is < 40 % busy (DESIGN.md section 4, profiles/)"}
 
     # ---- e2e: counts start every step in pinned host memory ----------------------------------------------
     e2e = None

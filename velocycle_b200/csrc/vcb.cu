@@ -33,6 +33,7 @@ struct CellParams {
   int H, Hw, Nx, velo, tabg;
 };
 
+constexpr int kCellEpiThreads = 256;
 constexpr int kTabWarps = 8;
 constexpr int kTabSlots = 16;  // 8 * ksteps(VCB_MAX_HARMONICS)
 
@@ -144,39 +145,37 @@ struct CellEpiParams {
   float* d_phi;
   float* d_cf;
   float* d_omega;
-  double* dnw_acc;  // [Nx*Kw], zeroed
+  double* dnw_part;  // [gridDim.x][Nx*Kw] per-block partial sums of d/dnu_omega (summed in order by the gene epilogue)
   long long Nc, Ncp;
   int n_part, NQ, Hw, Nx;
 };
 
 __global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
-  extern __shared__ double s_acc[];  // [Nx*Kw]
+  extern __shared__ double s_acc[];  // [warps][Nx*Kw]
   const bool velo = P.NQ == 3;
   const int Kw = 2 * P.Hw + 1;
   const int nacc = velo ? P.Nx * Kw : 0;
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) s_acc[i] = 0.0;
-  __syncthreads();
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  float pom = 0.f, phi = 0.f;
+  int x = -1;  // condition of this thread's cell; -1 = no cell
   if (c < P.Nc) {
     float q[3] = {0.f, 0.f, 0.f};
     for (int t = 0; t < P.n_part; ++t)
       for (int i = 0; i < P.NQ; ++i) q[i] += P.cellpart[((long long)t * P.Ncp + c) * P.NQ + i];
     float dphi = q[1];
     if (velo) {
-      const float phi = P.phi[c];
-      const int x = P.cond_id ? P.cond_id[c] : 0;
+      phi = P.phi[c];
+      x = P.cond_id ? P.cond_id[c] : 0;
       const float* nw = P.nu_omega + (long long)x * Kw;
-      const float pom = q[2];
+      pom = q[2];
       float domega_dphi = 0.f;
-      atomicAdd(&s_acc[x * Kw], (double)pom);
       for (int n = 1; n <= P.Hw; ++n) {
         float s, co;
         const float fn = (float)n;
         sincosf(fn * phi, &s, &co);
         domega_dphi = fmaf(nw[2 * n - 1], fn * co, domega_dphi);
         domega_dphi = fmaf(nw[2 * n], -fn * s, domega_dphi);
-        atomicAdd(&s_acc[x * Kw + 2 * n - 1], (double)(pom * s));
-        atomicAdd(&s_acc[x * Kw + 2 * n], (double)(pom * co));
       }
       dphi = fmaf(pom, domega_dphi, dphi);
       if (P.d_omega) P.d_omega[c] = pom;
@@ -184,9 +183,35 @@ __global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
     if (P.d_cf) P.d_cf[c] = q[0];
     if (P.d_phi) P.d_phi[c] = dphi;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x)
-    if (s_acc[i] != 0.0) atomicAdd(&P.dnw_acc[i], s_acc[i]);
+  // d/dnu_omega[x][h] = sum over the cells of condition x of d/domega * zeta_omega[h]: fp64 warp sums per condition
+  // (shuffles), parked per warp and added in warp order -- no atomics, so the result is reproducible bit for bit
+  if (velo) {
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int xx = 0; xx < P.Nx; ++xx) {
+      const bool any = __any_sync(full, x == xx);
+      const double w = (x == xx) ? (double)pom : 0.0;
+      for (int h = 0; h < Kw; ++h) {
+        double v = 0.0;
+        if (any) {
+          v = w;
+          if (h > 0) {
+            float s, co;
+            sincosf((float)((h + 1) / 2) * phi, &s, &co);
+            v *= (double)((h & 1) ? s : co);
+          }
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+        }
+        if (lane == 0) s_acc[(size_t)warp * nacc + xx * Kw + h] = v;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+      double t = 0.0;
+      for (int w = 0; w < nwarps; ++w) t += s_acc[(size_t)w * nacc + i];
+      P.dnw_part[(size_t)blockIdx.x * nacc + i] = t;
+    }
+  }
 }
 
 // ======================================================================================================
@@ -198,7 +223,8 @@ struct GeneEpiParams {
   const float* genepart;  // [n_split][ROWS][ld]
   const float* shape_inv;
   const float* dnu_acc;  // [Nb][Ng] or null
-  const double* dnw_acc;
+  const double* dnw_part;  // [n_cell_blocks][Nx*Kw]
+  int n_cell_blocks;
   vcb_spectrum_t spec_S, spec_U;
   float *lp_S, *lp_U, *d_nu, *d_dnu, *d_shape_inv, *d_logbeta, *d_gamma, *d_nu_omega;
   long long Nc, Ng, ld;
@@ -316,7 +342,20 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
   }
   if (blockIdx.x == 0 && P.velo && P.grad && P.d_nu_omega != nullptr) {
     const int n = P.Nx * (2 * P.Hw + 1);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) P.d_nu_omega[i] = (float)P.dnw_acc[i];
+    // fixed-order sum of the cell epilogue's per-block partials: thread t takes blocks t, t+T, ...; then T partials
+    __shared__ double s_red[kEpiGenes * kEpiLanes];
+    for (int i = 0; i < n; ++i) {
+      double t = 0.0;
+      for (int b = threadIdx.x; b < P.n_cell_blocks; b += blockDim.x) t += P.dnw_part[(size_t)b * n + i];
+      s_red[threadIdx.x] = t;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int j = 0; j < (int)blockDim.x; ++j) tot += s_red[j];
+        P.d_nu_omega[i] = (float)tot;
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -380,7 +419,8 @@ struct Plan {
   int np, nthr, tile_g, n_tiles, n_split, n_ring;
   int tabg, rows, NQ;
   long long n_groups, Ncp;
-  size_t off_tab, off_genepart, off_cellpart, off_dnuacc, off_dnwacc, total;
+  size_t off_tab, off_genepart, off_cellpart, off_dnuacc, off_dnwpart, total;
+  int n_cell_blocks;
   int smem;
 };
 
@@ -457,8 +497,9 @@ static Plan make_plan(const vcb_problem_t* p, bool velo) {
   off = align_up(off + (size_t)pl.n_tiles * pl.NQ * pl.Ncp * 4, 256);
   pl.off_dnuacc = off;
   off = align_up(off + (size_t)(p->Nb > 0 ? p->Nb : 0) * p->Ng * 4, 256);
-  pl.off_dnwacc = off;
-  off = align_up(off + (size_t)(p->Nx > 0 ? p->Nx : 1) * (2 * p->Hw + 1) * 8, 256);
+  pl.off_dnwpart = off;
+  pl.n_cell_blocks = (int)((p->Nc + kCellEpiThreads - 1) / kCellEpiThreads);
+  off = align_up(off + (size_t)(pl.n_cell_blocks > 0 ? pl.n_cell_blocks : 1) * (p->Nx > 0 ? p->Nx : 1) * (2 * p->Hw + 1) * 8, 256);
   pl.total = off;
   return pl;
 }
@@ -526,16 +567,12 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
   float* genepart = (float*)(ws + pl.off_genepart);
   float* cellpart = (float*)(ws + pl.off_cellpart);
   float* dnu_acc = p->Nb > 0 ? (float*)(ws + pl.off_dnuacc) : nullptr;
-  double* dnw_acc = (double*)(ws + pl.off_dnwacc);
+  double* dnw_part = (double*)(ws + pl.off_dnwpart);
   cudaError_t e;
 
   if (grad) {
     if (dnu_acc) {
       e = cudaMemsetAsync(dnu_acc, 0, (size_t)p->Nb * p->Ng * 4, st);
-      if (e != cudaSuccess) return (int)e;
-    }
-    if (velo) {
-      e = cudaMemsetAsync(dnw_acc, 0, (size_t)p->Nx * (2 * p->Hw + 1) * 8, st);
       if (e != cudaSuccess) return (int)e;
     }
   }
@@ -566,10 +603,10 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
   }
   if (grad && p->Nc > 0) {
     CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
-                     dnw_acc,  p->Nc,  pl.Ncp, pl.n_tiles, pl.NQ, p->Hw, velo ? p->Nx : 0};
-    const int bs = 256;
-    const size_t sm = velo ? (size_t)p->Nx * (2 * p->Hw + 1) * 8 : 0;
-    vcb_cell_epilogue_kernel<<<(unsigned)((p->Nc + bs - 1) / bs), bs, sm, st>>>(ce);
+                     dnw_part, p->Nc,  pl.Ncp, pl.n_tiles, pl.NQ, p->Hw, velo ? p->Nx : 0};
+    const int bs = kCellEpiThreads;
+    const size_t sm = velo ? (size_t)(bs / 32) * p->Nx * (2 * p->Hw + 1) * 8 : 0;
+    vcb_cell_epilogue_kernel<<<(unsigned)pl.n_cell_blocks, bs, sm, st>>>(ce);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -578,7 +615,8 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
     ge.genepart = genepart;
     ge.shape_inv = p->shape_inv;
     ge.dnu_acc = grad ? dnu_acc : nullptr;
-    ge.dnw_acc = dnw_acc;
+    ge.dnw_part = dnw_part;
+    ge.n_cell_blocks = (grad && p->Nc > 0) ? pl.n_cell_blocks : 0;
     ge.spec_S = p->spec_S;
     ge.spec_U = p->spec_U;
     ge.lp_S = p->lp_S;

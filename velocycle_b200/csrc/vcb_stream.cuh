@@ -495,21 +495,32 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     float2 pcf2[2] = {zero2, zero2}, pphi2[2] = {zero2, zero2}, pom2[2] = {zero2, zero2};
     const float2* cnt2 = reinterpret_cast<const float2*>(cnt);
 
-    // one row tile (16 genes x 8 cells) at a time: forward MMAs -> element terms -> backward MMAs, so that only one
-    // tile's accumulator fragments are live
+    // Row tiles (16 genes x 8 cells) are software-pipelined: the forward MMAs of tile mt+1 are issued before the
+    // element terms of tile mt, so that the tensor pipe's latency hides behind fp32 / MUFU work of the same warp;
+    // element terms -> backward MMAs of a tile stay together so that only two tiles' fragments are ever live.
+    float Cf[2][3][4];  // [pipeline slot][eta, d, omega*d''][fragment]
+    auto forward = [&](int mt, float (&C)[3][4]) {
 #pragma unroll
-    for (int mt = 0; mt < NT; ++mt) {
-      const int p = mt >> 1, t = mt & 1;
-      // ---- forward contractions on the tensor pipe -----------------------------------------------------
-      float Ce[4] = {0.f, 0.f, 0.f, 0.f}, Cd[4] = {0.f, 0.f, 0.f, 0.f}, Cw[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) C[j][i] = 0.f;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const uint4 a0 = s_aop[((mt * KS + ks) * 2 + 0) * 32], a1 = s_aop[((mt * KS + ks) * 2 + 1) * 32];
         const uint32_t am[4] = {a0.x, a0.y, a0.z, a0.w}, ax[4] = {a1.x, a1.y, a1.z, a1.w};
-        mma_split_fwd(Ce, am, ax, tb4[(SEC_F0 * KS + ks) * 32 + lane]);
-        if (NEED_D) mma_split_fwd(Cd, am, ax, tb4[(SEC_F1 * KS + ks) * 32 + lane]);
-        if (NEED_E) mma_split_fwd(Cw, am, ax, tb4[(SEC_F2 * KS + ks) * 32 + lane]);
+        mma_split_fwd(C[0], am, ax, tb4[(SEC_F0 * KS + ks) * 32 + lane]);
+        if (NEED_D) mma_split_fwd(C[1], am, ax, tb4[(SEC_F1 * KS + ks) * 32 + lane]);
+        if (NEED_E) mma_split_fwd(C[2], am, ax, tb4[(SEC_F2 * KS + ks) * 32 + lane]);
       }
+    };
+    forward(0, Cf[0]);
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+      const int p = mt >> 1, t = mt & 1;
+      if (mt + 1 < NT) forward(mt + 1, Cf[(mt + 1) & 1]);
+      float(&Ce)[4] = Cf[mt & 1][0];
+      float(&Cd)[4] = Cf[mt & 1][1];
+      float(&Cw)[4] = Cf[mt & 1][2];
       const float4 ga = s_gene[(mt * 2 + 0) * 8];
       const float2 nr_mt = f2(ga.x, ga.y);
       float2 gam_mt = one2, invb_mt = one2;
@@ -531,9 +542,10 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
           const long long g0 = gene_of(mt, 0);
           c0 = f2(const_term(g0, bc[cc]), const_term(g0 + 1, bc[cc]));
         }
-        const float2 eta = add2(f2(Ce[cc], Ce[2 + cc]), c0);
+        // (the accumulator fragment holds the gene pair in registers c[cc], c[2+cc]: the first operation on it is
+        //  issued per gene, its result lands in an aligned pair and everything after is packed f32x2)
         const float2 d = f2(Cd[cc], Cd[2 + cc]);
-        const float2 y = mul2(eta, l2e);
+        const float2 y = f2((Ce[cc] + c0.x) * kLog2e, (Ce[2 + cc] + c0.y) * kLog2e);
         const float2 u = ex2_2(y);
         const float2 s = add2(u, one2);
         const float2 LS = lg2_2(s);
@@ -548,7 +560,7 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
         }
         float2 g = zero2, w = zero2;
         if (VELO) {
-          const float2 a = fma2(d, f2s(om[cc]), gam_mt);
+          const float2 a = f2(fmaf(Cd[cc], om[cc], gam_mt.x), fmaf(Cd[2 + cc], om[cc], gam_mt.y));
           const float2 m = add2(f2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)), eps2);
           const float2 mb = mul2(m, invb_mt);
           const float2 uU = mul2(u, mb);
