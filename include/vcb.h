@@ -13,6 +13,12 @@
  *   vcb_count_histogram   <->  no reference counterpart; one-off data statistic that lets the
  *                              parameter-only lgamma/digamma terms of GammaPoisson.log_prob
  *                              (pyro/distributions/conjugate.py) leave the per-element loop.
+ *   vcb_expand_counts     <->  the device side of preprocessing.py:142-143 / 193-194 (248-249 / 308-309):
+ *                              `torch.tensor(S).to(device)` ... `.T.float()`.  The reference ships the dense
+ *                              count matrix to the device as 8-byte integers and widens it there; this entry
+ *                              point widens a compact host staging format (u8 with an overflow list, u16, i32)
+ *                              into the float32 cell-major layout the kernels stream, so a count matrix crosses
+ *                              PCIe at 1-2 bytes per entry instead of 4-8.
  *   vcb_clipped_adam      <->  pyro.optim.ClippedAdam.step (pyro/optim/clipped_adam.py), configured in
  *                              tutorials/Tutorial_Capolupo_HumanFibroblasts_OneSample.ipynb cell 27.
  *
@@ -39,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VCB_VERSION 100 /* 0.1.0 */
+#define VCB_VERSION 110 /* 0.1.1 */
 
 #define VCB_MAX_HARMONICS 5 /* gene / angular-speed harmonics compiled in: H in 0..5 */
 
@@ -137,6 +143,18 @@ int vcb_velocity_fwd_bwd(const vcb_problem_t* p, void* workspace, size_t workspa
  * status[0] is set non-zero if a value is negative, non-integer or >= B-1 (caller zeroes it too). */
 int vcb_count_histogram(const float* M, int64_t Nc, int64_t Ng, int64_t ld, int32_t B, uint32_t* hist,
                         int32_t* status, void* stream);
+
+/* Staging formats of vcb_expand_counts (src_dtype). */
+#define VCB_COUNTS_U8 1  /* one byte per entry; 255 = "see the overflow list" */
+#define VCB_COUNTS_U16 2 /* two bytes per entry */
+#define VCB_COUNTS_I32 4 /* four bytes per entry (the reference's anndata layers after astype(int)) */
+
+/* Widen `n` staged count entries (a whole number of [ld]-pitched rows, device memory, 16-byte aligned, n % 16 == 0
+ * or the tail is handled element-wise) to float32: dst[i] = (float)src[i].  Under VCB_COUNTS_U8 the `n_over` entries
+ * whose count is >= 255 are listed in (over_idx[j], over_val[j]) -- flat indices into dst, any order, no duplicates --
+ * and are written after the bulk pass on the same stream.  Exact for every count < 2^24. */
+int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst, const int64_t* over_idx,
+                      const float* over_val, int64_t n_over, void* stream);
 
 /* Multi-tensor ClippedAdam over one flat fp32 buffer of n elements:
  *   lr_t = lr0 * lrd^step (step counts from 1, read from device memory so that graphs replay),

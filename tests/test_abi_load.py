@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.vcb_version() == 100
+    assert lib.vcb_version() == 110
     assert lib.vcb_strerror(0) == b"ok"
     assert b"NULL" in lib.vcb_strerror(-1)
 

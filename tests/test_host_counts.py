@@ -1,0 +1,109 @@
+"""HostCounts: the compact pinned-host staging format of a count matrix and its widening on the device
+(``vcb_expand_counts``; replaces the int64 host->device copy + ``.float()`` of preprocessing.py:142-143, 193-194).
+Integer work: the round trip must be bit-exact."""
+import pytest
+import torch
+
+from velocycle_b200 import _lib
+from velocycle_b200.fused import HostCounts
+
+
+def _matrix(kind, Nc=777, ld=52, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "small":      # every count < 255: one byte each, no escapes
+        return torch.poisson(torch.full((Nc, ld), 2.0), generator=g)
+    if kind == "escapes":    # a few large counts: one byte each + (index, value) list
+        M = torch.poisson(torch.full((Nc, ld), 2.0), generator=g)
+        M[3, 5], M[Nc - 1, ld - 1], M[100, 0] = 255.0, 70000.0, 1093.0
+        return M
+    if kind == "wide":       # counts in the hundreds everywhere: two bytes each
+        return torch.poisson(torch.full((Nc, ld), 400.0), generator=g)
+    if kind == "huge":       # beyond 16 bits: four bytes each
+        M = torch.poisson(torch.full((Nc, ld), 400.0), generator=g)
+        M[0, 0] = 1.0e6
+        return M
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,fmt", [("small", _lib.VCB_COUNTS_U8), ("escapes", _lib.VCB_COUNTS_U8),
+                                      ("wide", _lib.VCB_COUNTS_U16), ("huge", _lib.VCB_COUNTS_I32)])
+def test_format_choice_and_host_packing(kind, fmt):
+    M = _matrix(kind)
+    h = HostCounts.from_tensor(M, chunk_rows=200)  # several chunks, ragged last one
+    assert h.fmt == fmt and h.shape == tuple(M.shape)
+    staged = h.staged.to(torch.int64)
+    if fmt == _lib.VCB_COUNTS_U8:
+        esc = M >= 255
+        assert torch.equal(staged[~esc], M[~esc].to(torch.int64))
+        assert bool((staged[esc] == 255).all())
+        if esc.any():
+            order = torch.argsort(h.over_idx)
+            assert torch.equal(h.over_idx[order], esc.reshape(-1).nonzero().reshape(-1))
+            assert torch.equal(h.over_val[order], M.reshape(-1)[esc.reshape(-1)])
+            assert h.nbytes == M.numel() + 12 * int(esc.sum())
+        else:
+            assert h.over_idx is None and h.nbytes == M.numel()
+    else:
+        assert torch.equal(staged, M.to(torch.int64))
+        assert h.nbytes == M.numel() * (2 if fmt == _lib.VCB_COUNTS_U16 else 4)
+
+
+def test_unrepresentable_counts_are_refused():
+    M = _matrix("small")
+    M[1, 1] = float(2 ** 24)
+    with pytest.raises(_lib.VcbError):
+        HostCounts.from_tensor(M)
+
+
+def test_upload_refuses_cpu_destination():
+    h = HostCounts.from_tensor(_matrix("small"))
+    with pytest.raises(_lib.VcbError):
+        h.upload(torch.zeros(h.shape))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["small", "escapes", "wide", "huge"])
+@pytest.mark.parametrize("shape", [(777, 52), (1, 4), (4099, 2000)])
+def test_device_round_trip_is_bit_exact(kind, shape):
+    M = _matrix(kind, *shape, seed=3) if shape[0] > 200 else _matrix("small", *shape, seed=3)
+    h = HostCounts.from_tensor(M)
+    dst = torch.full(M.shape, -1.0, device="cuda")
+    h.upload(dst)
+    h.upload(dst)  # idempotent, reuses the device staging buffers
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), M)
+
+
+@pytest.mark.gpu
+def test_from_device_tensor_and_kernel_sees_identical_counts():
+    """Packing from the device-resident matrix (what bench.py's e2e leg does) and feeding the widened copy to the
+    fused path gives the same log-probs and gradients, bit for bit."""
+    from velocycle_b200.fused import PackedCounts, fused_elbo_grad
+    from velocycle_b200.synthetic import make_synthetic
+
+    d = make_synthetic(3000, 203, H=2, Hw=1, Nb=1, Nx=1, seed=7, device="cuda")
+    d.S[17, 3] = 4321.0
+    counts = PackedCounts(d.S, d.U, d.Ng, d.batch_id, d.cond_id)
+    args = (d.phi, d.cf, d.nu, None, d.shape_inv, d.logbeta, torch.exp(d.loggamma), d.nu_omega)
+    ref = {k: v.clone() for k, v in fused_elbo_grad(counts, *args, grad=True).items()}
+    hS, hU = HostCounts.from_tensor(d.S), HostCounts.from_tensor(d.U)
+    assert hS.fmt == _lib.VCB_COUNTS_U8 and hS.over_idx is not None
+    S2, U2 = torch.empty_like(d.S), torch.empty_like(d.U)
+    hS.upload(S2)
+    hU.upload(U2)
+    assert torch.equal(S2, d.S) and torch.equal(U2, d.U)
+    out = fused_elbo_grad(PackedCounts(S2, U2, d.Ng, d.batch_id, d.cond_id), *args, grad=True)
+    for k in ref:
+        if k.startswith("_"):  # scratch buffers kept alive with the result
+            continue
+        assert torch.equal(ref[k], out[k]), (k, float((ref[k] - out[k]).abs().max()), float(ref[k].abs().max()))
+
+
+@pytest.mark.gpu
+def test_expand_counts_argument_errors():
+    lib = _lib.load()
+    t = torch.zeros(64, device="cuda")
+    assert lib.vcb_expand_counts(None, 1, 16, t.data_ptr(), None, None, 0, None) == -1
+    assert lib.vcb_expand_counts(t.data_ptr(), 3, 16, t.data_ptr(), None, None, 0, None) == -2
+    assert lib.vcb_expand_counts(t.data_ptr() + 4, 1, 16, t.data_ptr(), None, None, 0, None) == -3
+    assert lib.vcb_expand_counts(t.data_ptr(), 2, 16, t.data_ptr(), None, None, 5, None) == -1  # overflow list only with u8

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvcb.so")
 VCB_FLAG_GRAD = 1
 VCB_FLAG_LGAMMA_INLINE = 2
 VCB_MAX_HARMONICS = 5
+VCB_COUNTS_U8, VCB_COUNTS_U16, VCB_COUNTS_I32 = 1, 2, 4
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -48,6 +49,7 @@ EXPORTS = (
     "vcb_phase_fwd_bwd",
     "vcb_velocity_fwd_bwd",
     "vcb_count_histogram",
+    "vcb_expand_counts",
     "vcb_clipped_adam",
 )
 
@@ -82,6 +84,10 @@ def load() -> C.CDLL:
     lib.vcb_count_histogram.restype = C.c_int
     lib.vcb_count_histogram.argtypes = [
         C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+    ]
+    lib.vcb_expand_counts.restype = C.c_int
+    lib.vcb_expand_counts.argtypes = [
+        C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
     ]
     lib.vcb_clipped_adam.restype = C.c_int
     lib.vcb_clipped_adam.argtypes = [

@@ -390,6 +390,42 @@ __global__ void vcb_count_histogram_kernel(const float* __restrict__ M, long lon
 }
 
 // ======================================================================================================
+// Count staging formats -> float32 (vcb_expand_counts).  Pure streaming: 16 entries per thread and iteration,
+// 128-bit loads and stores, grid = a few CTAs per SM.
+// ======================================================================================================
+template <typename T>
+__device__ __forceinline__ float count_to_float(T v) {
+  return (float)v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) vcb_expand_counts_kernel(const T* __restrict__ src, float* __restrict__ dst,
+                                                               long long n) {
+  constexpr int V = 16 / sizeof(T);  // entries per 16-byte load
+  const long long nvec = n / V;
+  const uint4* src4 = reinterpret_cast<const uint4*>(src);
+  float4* dst4 = reinterpret_cast<float4*>(dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 raw = __ldcs(src4 + i);
+    T v[V];
+    *reinterpret_cast<uint4*>(v) = raw;
+#pragma unroll
+    for (int j = 0; j < V / 4; ++j)
+      __stcs(dst4 + i * (V / 4) + j, make_float4(count_to_float(v[4 * j]), count_to_float(v[4 * j + 1]),
+                                                 count_to_float(v[4 * j + 2]), count_to_float(v[4 * j + 3])));
+  }
+  for (long long i = nvec * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = count_to_float(src[i]);
+}
+
+__global__ void vcb_scatter_overflow_kernel(const long long* __restrict__ idx, const float* __restrict__ val,
+                                            long long n, float* __restrict__ dst) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[idx[i]] = val[i];
+}
+
+// ======================================================================================================
 // Fused multi-tensor ClippedAdam (pyro/optim/clipped_adam.py semantics, lr decayed before use).
 // ======================================================================================================
 __global__ void vcb_adam_tick_kernel(long long* step) { *step += 1; }
@@ -696,6 +732,33 @@ int vcb_count_histogram(const float* M, int64_t Nc, int64_t Ng, int64_t ld, int3
   vcb::vcb_count_histogram_kernel<<<grid, bs, 0, (cudaStream_t)stream>>>(M, Nc, Ng, ld, B, hist, status,
                                                                         cells_per_block);
   return (int)cudaGetLastError();
+}
+
+int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst, const int64_t* over_idx,
+                      const float* over_val, int64_t n_over, void* stream) {
+  if (!src || !dst) return VCB_ERR_NULL;
+  if (n < 0 || n_over < 0) return VCB_ERR_SIZE;
+  if (n_over > 0 && (!over_idx || !over_val || src_dtype != VCB_COUNTS_U8)) return VCB_ERR_NULL;
+  if ((((uintptr_t)src) & 15) != 0 || (((uintptr_t)dst) & 15) != 0) return VCB_ERR_ALIGN;
+  if (n == 0) return VCB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int bs = 256;
+  const unsigned blocks = 148 * 8;
+  switch (src_dtype) {
+    case VCB_COUNTS_U8: vcb::vcb_expand_counts_kernel<uint8_t><<<blocks, bs, 0, st>>>((const uint8_t*)src, dst, n); break;
+    case VCB_COUNTS_U16: vcb::vcb_expand_counts_kernel<uint16_t><<<blocks, bs, 0, st>>>((const uint16_t*)src, dst, n); break;
+    case VCB_COUNTS_I32: vcb::vcb_expand_counts_kernel<int32_t><<<blocks, bs, 0, st>>>((const int32_t*)src, dst, n); break;
+    default: return VCB_ERR_SIZE;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (n_over > 0) {
+    long long b = (n_over + bs - 1) / bs;
+    if (b > blocks) b = blocks;
+    vcb::vcb_scatter_overflow_kernel<<<(unsigned)b, bs, 0, st>>>((const long long*)over_idx, over_val, n_over, dst);
+    e = cudaGetLastError();
+  }
+  return (int)e;
 }
 
 int vcb_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_dev,

@@ -9,6 +9,8 @@ PyTorch is plumbing here (device memory, streams, autograd wiring); the arithmet
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, Optional
@@ -19,7 +21,7 @@ from . import _lib
 from ._lib import VcbProblem, VcbSpectrum, VCB_FLAG_GRAD, VCB_FLAG_LGAMMA_INLINE
 from .sharding import allreduce_flat_
 
-__all__ = ["CountSpectrum", "PackedCounts", "fused_elbo_grad", "FusedCycleNB", "fused_cycle_nb"]
+__all__ = ["CountSpectrum", "HostCounts", "PackedCounts", "fused_elbo_grad", "FusedCycleNB", "fused_cycle_nb"]
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -85,6 +87,102 @@ class CountSpectrum:
             val = torch.zeros(1, dtype=torch.float32, device=dev)
             mult = torch.zeros(1, dtype=torch.float32, device=dev)
         return CountSpectrum(off.contiguous(), val.contiguous(), mult.contiguous(), lgk1.contiguous(), kmax)
+
+
+class HostCounts:
+    """Pinned-host staging of one count matrix in the narrowest exact integer format, and its upload.
+
+    The reference ships the dense count matrix to the device as int64 and widens it there
+    (``preprocessing.py:142-143, 193-194``: ``torch.tensor(S).to(device)`` ... ``.T.float()``): 8 bytes per entry
+    over PCIe.  Counts are small integers, so the staging copy here holds one byte per entry (255 = escape, the
+    few larger entries travel as an (index, value) list), two bytes when more than 2 % of the entries would
+    escape, or four; ``upload`` copies it to the device and ``vcb_expand_counts`` widens it into the float32
+    cell-major ``[Nc][ld]`` matrix the kernels stream.  Every count below 2**24 round-trips exactly.
+    """
+
+    ESCAPE = 255
+
+    def __init__(self, staged: torch.Tensor, fmt: int, shape, over_idx=None, over_val=None):
+        self.staged, self.fmt, self.shape = staged, fmt, tuple(shape)
+        self.over_idx, self.over_val = over_idx, over_val
+        self._dev = None  # device staging buffers, created on first upload
+
+    @property
+    def nbytes(self) -> int:
+        """Bytes that cross PCIe per upload."""
+        n = self.staged.numel() * self.staged.element_size()
+        if self.over_idx is not None:
+            n += self.over_idx.numel() * 8 + self.over_val.numel() * 4
+        return n
+
+    @staticmethod
+    def choose_format(max_count: float, escape_fraction: float) -> int:
+        if max_count >= 2 ** 24:
+            raise _lib.VcbError("counts >= 2**24 are not exactly representable in the float32 device layout")
+        if max_count < HostCounts.ESCAPE or escape_fraction <= 0.02:
+            return _lib.VCB_COUNTS_U8
+        return _lib.VCB_COUNTS_U16 if max_count < 2 ** 16 else _lib.VCB_COUNTS_I32
+
+    @classmethod
+    def from_tensor(cls, M: torch.Tensor, chunk_rows: int = 1 << 16) -> "HostCounts":
+        """``M``: (Nc, ld) non-negative integer-valued matrix (any real dtype, CPU or CUDA), already padded to the
+        device pitch.  Packed chunk by chunk on the device the data lives on; the staging copy is pinned."""
+        assert M.dim() == 2
+        Nc, ld = M.shape
+        mx = float(M.max()) if M.numel() else 0.0
+        n_esc = 0
+        for r0 in range(0, Nc, chunk_rows):
+            n_esc += int((M[r0: r0 + chunk_rows] >= cls.ESCAPE).sum())
+        fmt = cls.choose_format(mx, n_esc / max(1, M.numel()))
+        tdt = {_lib.VCB_COUNTS_U8: torch.uint8, _lib.VCB_COUNTS_U16: torch.uint16, _lib.VCB_COUNTS_I32: torch.int32}[fmt]
+        pin = torch.cuda.is_available()
+        staged = torch.empty((Nc, ld), dtype=tdt, pin_memory=pin)
+        idx, val = [], []
+        for r0 in range(0, Nc, chunk_rows):
+            blk = M[r0: r0 + chunk_rows]
+            if fmt == _lib.VCB_COUNTS_U8:
+                esc = blk >= cls.ESCAPE
+                if n_esc:
+                    nz = esc.reshape(-1).nonzero().reshape(-1)
+                    idx.append((nz + r0 * ld).to(torch.int64).cpu())
+                    val.append(blk.reshape(-1)[nz].to(torch.float32).cpu())
+                staged[r0: r0 + chunk_rows].copy_(torch.where(esc, cls.ESCAPE, blk).to(torch.uint8))
+            elif fmt == _lib.VCB_COUNTS_U16:
+                staged[r0: r0 + chunk_rows].copy_(blk.to(torch.int32).to(torch.uint16))
+            else:
+                staged[r0: r0 + chunk_rows].copy_(blk.to(torch.int32))
+        over_idx = over_val = None
+        if fmt == _lib.VCB_COUNTS_U8 and n_esc:
+            over_idx = torch.cat(idx)
+            over_val = torch.cat(val)
+            if pin:
+                over_idx, over_val = over_idx.pin_memory(), over_val.pin_memory()
+        return cls(staged, fmt, (Nc, ld), over_idx, over_val)
+
+    def upload(self, dst: torch.Tensor) -> None:
+        """H2D copy of the staging buffer + widening into ``dst`` (float32 CUDA (Nc, ld), contiguous), all on the
+        current stream; nothing synchronises."""
+        if not dst.is_cuda:
+            raise _lib.VcbError("HostCounts.upload needs a CUDA destination: velocycle_b200 has no CPU path")
+        assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape) == self.shape
+        dev = dst.device
+        if self._dev is None or self._dev[0].device != dev:
+            d_st = torch.empty(self.staged.shape, dtype=self.staged.dtype, device=dev)
+            d_i = d_v = None
+            if self.over_idx is not None:
+                d_i = torch.empty_like(self.over_idx, device=dev)
+                d_v = torch.empty_like(self.over_val, device=dev)
+            self._dev = (d_st, d_i, d_v)
+        d_st, d_i, d_v = self._dev
+        d_st.copy_(self.staged, non_blocking=True)
+        n_over = 0
+        if d_i is not None:
+            d_i.copy_(self.over_idx, non_blocking=True)
+            d_v.copy_(self.over_val, non_blocking=True)
+            n_over = d_i.numel()
+        lib = _lib.load()
+        _lib.check(lib.vcb_expand_counts(d_st.data_ptr(), self.fmt, dst.numel(), dst.data_ptr(), _ptr(d_i), _ptr(d_v),
+                                         n_over, torch.cuda.current_stream(dev).cuda_stream), "vcb_expand_counts")
 
 
 class PackedCounts:
@@ -255,6 +353,8 @@ def fused_elbo_grad(
         p.ev_stream_begin, p.ev_stream_end = ev
     ws_bytes = lib.vcb_workspace_bytes(C.byref(p))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    if os.environ.get("VCB_DEBUG_POISON_WS"):  # every byte 0xFF = NaN: an uninitialised read shows up in the outputs
+        ws.fill_(255)
     fn = lib.vcb_velocity_fwd_bwd if velocity else lib.vcb_phase_fwd_bwd
     _lib.check(fn(C.byref(p), ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream),
                "vcb_velocity_fwd_bwd" if velocity else "vcb_phase_fwd_bwd")
