@@ -45,7 +45,7 @@
 namespace vcb {
 
 constexpr int kGroupCells = 8;  // cells per ring stage = the n extent (forward) / k extent (backward) of the MMAs
-constexpr int kCountDepth = 5;  // count groups in flight per thread (5 x 32 KB per 512-thread CTA)
+constexpr int kCountDepth = 4;  // count groups in flight per thread (4 x 32 KB per 512-thread CTA)
 constexpr int kMaxStages = 16;  // the table ring is as deep as the rest of shared memory allows, up to this
 constexpr int kSmemHeader = 512;
 
@@ -95,7 +95,7 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int H, bool velo, int n
   StreamSmem L;
   int off = kSmemHeader;  // mbarriers
   L.part_off = off;
-  off += n_ring * nwarps * kGroupCells * (velo ? 3 : 2) * 4;
+  off += n_ring * nwarps * (velo ? 3 : 2) * 32 * 4;  // cell partials: [slot][warp][quantity][lane]
   off = (off + 127) / 128 * 128;
   L.gene_off = off;  // per-gene parameters: [warp][row tile][2][grp] float4
   off += nwarps * 2 * npair * 2 * 8 * 16;
@@ -375,12 +375,13 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     ldS[p] = reinterpret_cast<const char*>(P.S + off);
     ldU[p] = reinterpret_cast<const char*>((VELO ? P.U : P.S) + off);
   }
-  long long ld_rows_left = P.Nc - G0 * R;  // rows from the next stage's first row to the end of the matrix
-  int ld_left = n_stages;                  // stages still to load
-  auto load_counts = [&](int d) {          // next stage into depth slot d (stages are loaded in order)
-    if (ld_left > 0) {
+  // stages [0, n_whole) of this CTA lie entirely inside the matrix; only the very last group of the matrix can be ragged
+  const int n_whole = (int)((P.Nc / R > G0 ? P.Nc / R - G0 : 0) < (long long)n_stages ? (P.Nc / R > G0 ? P.Nc / R - G0 : 0)
+                                                                                       : (long long)n_stages);
+  auto load_counts = [&](int st, int d) {  // stage st (loaded in order) into depth slot d
+    if (st < n_stages) {
       uint32_t dst = s_cnt_ld + (uint32_t)d * (NLD * slot_bytes);
-      if (ld_rows_left >= R) {  // CTA-uniform; only the very last group of the matrix can be ragged
+      if (st < n_whole) {  // CTA-uniform
 #pragma unroll
         for (int mat = 0; mat < NMAT; ++mat)
 #pragma unroll
@@ -391,13 +392,14 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
               dst += slot_bytes;
             }
       } else {
+        const long long rows_left = P.Nc - (G0 + st) * R;
 #pragma unroll
         for (int mat = 0; mat < NMAT; ++mat)
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
             for (int p = 0; p < NPAIR; ++p) {
-              const bool ok = 4 * cc + l_row < ld_rows_left;
+              const bool ok = 4 * cc + l_row < rows_left;
               cp_async16(dst, ok ? (mat ? ldU[p] : ldS[p]) + (cc ? half_off : 0u) : reinterpret_cast<const char*>(P.S),
                          ok ? ld_sz[p] : 0u);
               dst += slot_bytes;
@@ -408,8 +410,6 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
         ldS[p] += row_step;
         ldU[p] += row_step;
       }
-      ld_rows_left -= R;
-      --ld_left;
     }
     cp_async_commit();  // one group per stage, empty past the end: wait_group counts stay uniform
   };
@@ -429,22 +429,27 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
   }
   __syncthreads();
   float* const cellpart_t = P.cellpart + (long long)tile * P.Ncp * NQ;
-  // sum the per-warp cell partials of a finished stage in warp order and store them (whole warp)
+  // Cell partials of a stage: every lane parks NQ values for ONE cell (q + 4*(lane/16)), summed over its 4 genes and
+  // one shuffle level; the warp that re-issues the slot adds the 4 lanes x nwarps terms of each of the 8*NQ outputs in
+  // a fixed order (deterministic) and stores them.  (A full butterfly per warp and group cost 15 % of the loop.)
   auto flush_partials = [&](int st, int slot) {
     if (lane < R * NQ) {
-      const float* src = s_part + (size_t)slot * nwarps * (R * NQ) + lane;
+      const int cell = lane / NQ, i = lane - cell * NQ;
+      const float* src = s_part + (size_t)slot * nwarps * (NQ * 32) + i * 32 + (cell & 3) + 16 * (cell >> 2);
       float s = 0.f;
-      for (int w = 0; w < nwarps; ++w) s += src[w * (R * NQ)];
+      for (int w = 0; w < nwarps; ++w) {
+        const float* sw = src + w * (NQ * 32);
+        s += (sw[0] + sw[4]) + (sw[8] + sw[12]);
+      }
       cellpart_t[(G0 + st) * (R * NQ) + lane] = s;
     }
   };
   // issue cursor over this warp's stages: stage i_next = i_k*NS + i_slot; i_need = the stage that must have left
   // the slot (i_next - NS), pushed out of reach once the warp has nothing more to issue
   int i_next = warp, i_slot = warp % NS, i_k = warp / NS;
-  int consumed = 0;  // stages this warp has finished
   int i_need = i_next < n_stages ? i_next - NS : 0x3fffffff;
   const uint32_t tab_bytes = (uint32_t)TABG * 4u;
-  auto issue_table = [&]() -> bool {  // warp-uniform; never blocks; true if a stage was issued
+  auto issue_table = [&](int consumed) -> bool {  // consumed = stages this warp has finished; warp-uniform; never blocks
     // A parity wait only distinguishes adjacent phases: do not look at done[] before this warp itself has
     // arrived for stage i_need (with fewer slots than warps its next stage is two phases ahead).
     if (i_need >= consumed) return false;
@@ -468,9 +473,9 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     i_need = i_next < n_stages ? i_next - NS : 0x3fffffff;
     return true;
   };
-  while (i_k == 0 && issue_table()) {}  // prologue: the slots are fresh
+  while (i_k == 0 && issue_table(0)) {}  // prologue: the slots are fresh
 #pragma unroll
-  for (int s = 0; s < D; ++s) load_counts(s);
+  for (int s = 0; s < D; ++s) load_counts(s, s);
 
   const float2 one2 = f2s(1.f), neg1 = f2s(-1.f), l2e = f2s(kLog2e), eps2 = f2s(1e-5f);
   int c_slot = 0, c_phase = 0, c_d = 0;  // consumer cursor: table slot / parity, count depth slot
@@ -637,8 +642,9 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     {
       uint32_t spins = 0;
       while (!__all_sync(0xffffffffu, mbar_try_wait(full0 + 8 * c_slot, (uint32_t)c_phase))) {
-        issue_table();
-        if (++spins > (1u << 24)) __trap();
+        issue_table(st);
+        __nanosleep(128);  // the table is not there yet: leave the issue slots to the warps that have work
+        if (++spins > (1u << 22)) __trap();
       }
     }
     cp_async_wait<D - 1>();  // this lane's loads of stage st have landed ...
@@ -666,23 +672,13 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     }
 
     if (GRAD) {
-      // sums over the warp's genes: the lane holds cells q and q+4; first swap halves so that lanes 0-15 keep
-      // cell q and lanes 16-31 cell q+4, then add over the remaining grp bits
+      // the lane holds partial sums for the cells q and q+4: swap halves so that lanes 0-15 keep cell q and lanes
+      // 16-31 cell q+4, and park the result; the remaining 4 lanes x nwarps terms are added when the slot is drained
       const bool up = (lane & 16) != 0;
-      float v[NQ];
-      v[0] = (up ? pcf[1] : pcf[0]) + __shfl_xor_sync(0xffffffffu, up ? pcf[0] : pcf[1], 16);
-      v[1] = (up ? pphi[1] : pphi[0]) + __shfl_xor_sync(0xffffffffu, up ? pphi[0] : pphi[1], 16);
-      if (VELO) v[NQ - 1] = (up ? pom[1] : pom[0]) + __shfl_xor_sync(0xffffffffu, up ? pom[0] : pom[1], 16);
-#pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 8);
-        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 4);
-      }
-      if ((lane & 12) == 0) {
-        float* dst = s_part + ((size_t)c_slot * nwarps + warp) * (R * NQ) + (q + 4 * (lane >> 4)) * NQ;
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) dst[i] = v[i];
-      }
+      float* dst = s_part + ((size_t)c_slot * nwarps + warp) * (NQ * 32) + lane;
+      dst[0] = (up ? pcf[1] : pcf[0]) + __shfl_xor_sync(0xffffffffu, up ? pcf[0] : pcf[1], 16);
+      dst[32] = (up ? pphi[1] : pphi[0]) + __shfl_xor_sync(0xffffffffu, up ? pphi[0] : pphi[1], 16);
+      if (VELO) dst[(NQ - 1) * 32] = (up ? pom[1] : pom[0]) + __shfl_xor_sync(0xffffffffu, up ? pom[0] : pom[1], 16);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(done0 + 8 * c_slot);  // this warp no longer needs the slot (release: partials are visible)
@@ -690,10 +686,9 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
       c_slot = 0;
       c_phase ^= 1;
     }
-    consumed = st + 1;
-    load_counts(c_d);  // refill the count slot this warp has just consumed
+    load_counts(st + D, c_d);  // refill the count slot this warp has just consumed
     if (++c_d == D) c_d = 0;
-    issue_table();
+    issue_table(st + 1);
   }
   cp_async_wait<0>();
 
