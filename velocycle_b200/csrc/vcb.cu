@@ -9,6 +9,7 @@
 
 #include "vcb_common.cuh"
 #include "vcb_stream.cuh"
+#include "vcb_umma.cuh"
 
 #ifndef VCB_DEFAULT_NP
 #define VCB_DEFAULT_NP 1
@@ -230,6 +231,7 @@ struct GeneEpiParams {
   long long Nc, Ng, ld;
   int n_split, H, Nb, Nx, Hw;
   int velo, grad, lginline;
+  int dnu_rows;  // single batch, d/ddnu = the constant column of d/dnu (tcgen05 path): no atomics buffer
 };
 
 constexpr int kEpiGenes = 8;
@@ -319,7 +321,9 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
     }
     if (P.grad) {
       double dnu0 = s_rows[ROW_DNU][gx];
-      if (P.Nb > 0 && P.dnu_acc != nullptr) {
+      if (P.dnu_rows) {
+        if (P.d_dnu) P.d_dnu[g] = (float)dnu0;
+      } else if (P.Nb > 0 && P.dnu_acc != nullptr) {
         dnu0 = 0.0;
         for (int b = 0; b < P.Nb; ++b) {
           const float v = P.dnu_acc[(long long)b * P.Ng + g];
@@ -540,6 +544,60 @@ static Plan make_plan(const vcb_problem_t* p, bool velo) {
   return pl;
 }
 
+// ---- tcgen05 path (vcb_umma.cuh): velocity model with gradients, H <= 3, at most one batch -----------------------------
+struct UmmaPlan {
+  int n_tiles, n_split, rows;
+  long long n_chunks, Ncp;
+  size_t off_tabF, off_tabB, off_omega, off_zero, off_genepart, off_cellpart, off_dnwpart, total;
+  int n_cell_blocks;
+};
+
+static int stream_kernel_choice() {  // 0 = mma.sync kernel, 1 = tcgen05 kernel where it applies
+  static int c = -1;
+  if (c < 0) {
+    const char* e = getenv("VCB_STREAM_KERNEL");
+    c = (e && e[0] == 'u') ? 1 : 0;
+  }
+  return c;
+}
+
+static bool umma_applies(const vcb_problem_t* p, bool velo) {
+  return velo && (p->flags & VCB_FLAG_GRAD) && !(p->flags & VCB_FLAG_LGAMMA_INLINE) && p->H <= 3 && p->Nb <= 1 && p->Nc > 0;
+}
+
+static UmmaPlan make_plan_umma(const vcb_problem_t* p) {
+  UmmaPlan pl{};
+  pl.n_tiles = (int)((p->ld + umma::GT - 1) / umma::GT);
+  pl.n_chunks = (p->Nc + umma::NC - 1) / umma::NC;
+  pl.Ncp = pl.n_chunks * umma::NC;
+  long long ns = sm_count() / pl.n_tiles;
+  if (ns > pl.n_chunks) ns = pl.n_chunks;
+  if (ns < 1) ns = 1;
+  pl.n_split = (int)ns;
+  pl.rows = gene_rows(p->H);
+  size_t off = 0;
+  pl.off_tabF = off;
+  off = align_up(off + (size_t)pl.n_chunks * umma::TABF_BYTES, 256);
+  pl.off_tabB = off;
+  off = align_up(off + (size_t)pl.n_chunks * umma::TABB_BYTES, 256);
+  pl.off_omega = off;
+  off = align_up(off + (size_t)pl.Ncp * 4, 256);
+  pl.off_zero = off;
+  off = align_up(off + (size_t)umma::GT * 4, 256);
+  pl.off_genepart = off;
+  off = align_up(off + (size_t)(2 * pl.n_split) * pl.rows * p->ld * 4, 256);
+  pl.off_cellpart = off;
+  off = align_up(off + (size_t)pl.n_tiles * 3 * pl.Ncp * 4, 256);
+  pl.off_dnwpart = off;
+  pl.n_cell_blocks = (int)((p->Nc + kCellEpiThreads - 1) / kCellEpiThreads);
+  off = align_up(off + (size_t)(pl.n_cell_blocks > 0 ? pl.n_cell_blocks : 1) * (p->Nx > 0 ? p->Nx : 1) * (2 * p->Hw + 1) * 8, 256);
+  pl.total = off;
+  return pl;
+}
+
+cudaError_t vcb_launch_umma_tables(const umma::TableParams& tp, cudaStream_t st);
+cudaError_t vcb_launch_umma_stream(const umma::Params& sp, int n_tiles, int n_split, cudaStream_t st);
+
 static int validate(const vcb_problem_t* p, bool velo) {
   if (p == nullptr) return VCB_ERR_NULL;
   if (p->Nc < 0 || p->Ng <= 0 || p->ld < p->Ng || p->Nc > (1LL << 40) || p->Ng > (1LL << 24)) return VCB_ERR_SIZE;
@@ -588,12 +646,89 @@ static cudaError_t launch_stream(int H, bool velo, bool grad, bool lgi, int np, 
   }
 }
 
+// The tcgen05 path: table kernel -> streaming kernel -> the same two epilogues (they only see partial-sum buffers).
+static int run_umma(const vcb_problem_t* p, void* workspace, size_t ws_bytes, void* stream) {
+  const UmmaPlan pl = make_plan_umma(p);
+  if (ws_bytes < pl.total) return VCB_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  float* tabF = (float*)(ws + pl.off_tabF);
+  float* tabB = (float*)(ws + pl.off_tabB);
+  float* omega = (float*)(ws + pl.off_omega);
+  float* zero = (float*)(ws + pl.off_zero);
+  float* genepart = (float*)(ws + pl.off_genepart);
+  float* cellpart = (float*)(ws + pl.off_cellpart);
+  double* dnw_part = (double*)(ws + pl.off_dnwpart);
+  cudaError_t e;
+  umma::TableParams tp{p->phi, p->cf, p->cond_id, p->nu_omega, tabF, tabB, omega, zero, p->Nc, pl.n_chunks, p->H, p->Hw};
+  e = vcb_launch_umma_tables(tp, st);
+  if (e != cudaSuccess) return (int)e;
+  {
+    umma::Params sp{p->S, p->U, tabF, tabB, omega, zero, p->nu, p->Nb > 0 ? p->dnu : nullptr, p->shape_inv, p->logbeta, p->gamma,
+                    genepart, cellpart, p->Nc, p->Ng, p->ld, pl.Ncp, pl.n_split, p->H, pl.rows};
+    unsigned ev_flags = cudaEventRecordDefault;
+    if (p->ev_stream_begin || p->ev_stream_end) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+        ev_flags = cudaEventRecordExternal;
+    }
+    if (p->ev_stream_begin) cudaEventRecordWithFlags((cudaEvent_t)p->ev_stream_begin, st, ev_flags);
+    e = vcb_launch_umma_stream(sp, pl.n_tiles, pl.n_split, st);
+    if (e != cudaSuccess) return (int)e;
+    if (p->ev_stream_end) cudaEventRecordWithFlags((cudaEvent_t)p->ev_stream_end, st, ev_flags);
+  }
+  {
+    CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
+                     dnw_part, p->Nc,  pl.Ncp, pl.n_tiles, 3, p->Hw, p->Nx};
+    const int bs = kCellEpiThreads;
+    const size_t sm = (size_t)(bs / 32) * p->Nx * (2 * p->Hw + 1) * 8;
+    vcb_cell_epilogue_kernel<<<(unsigned)pl.n_cell_blocks, bs, sm, st>>>(ce);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    GeneEpiParams ge{};
+    ge.genepart = genepart;
+    ge.shape_inv = p->shape_inv;
+    ge.dnu_acc = nullptr;
+    ge.dnw_part = dnw_part;
+    ge.n_cell_blocks = pl.n_cell_blocks;
+    ge.spec_S = p->spec_S;
+    ge.spec_U = p->spec_U;
+    ge.lp_S = p->lp_S;
+    ge.lp_U = p->lp_U;
+    ge.d_nu = p->d_nu;
+    ge.d_dnu = p->d_dnu;
+    ge.d_shape_inv = p->d_shape_inv;
+    ge.d_logbeta = p->d_logbeta;
+    ge.d_gamma = p->d_gamma;
+    ge.d_nu_omega = p->d_nu_omega;
+    ge.Nc = p->Nc;
+    ge.Ng = p->Ng;
+    ge.ld = p->ld;
+    ge.n_split = 2 * pl.n_split;
+    ge.H = p->H;
+    ge.Nb = p->Nb;
+    ge.Nx = p->Nx;
+    ge.Hw = p->Hw;
+    ge.velo = 1;
+    ge.grad = 1;
+    ge.lginline = 0;
+    ge.dnu_rows = p->Nb > 0 ? 1 : 0;
+    vcb_gene_epilogue_kernel<<<(unsigned)((p->Ng + kEpiGenes - 1) / kEpiGenes), kEpiGenes * kEpiLanes, 0, st>>>(ge);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return VCB_OK;
+}
+
 static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_bytes, void* stream) {
   int rc = validate(p, velo);
   if (rc != VCB_OK) return rc;
-  const Plan pl = make_plan(p, velo);
   if (workspace == nullptr) return VCB_ERR_NULL;
   if (((uintptr_t)workspace & 15) != 0) return VCB_ERR_ALIGN;
+  if (stream_kernel_choice() == 1 && umma_applies(p, velo)) return run_umma(p, workspace, ws_bytes, stream);
+  const Plan pl = make_plan(p, velo);
   if (ws_bytes < pl.total) return VCB_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const bool grad = (p->flags & VCB_FLAG_GRAD) != 0;
@@ -710,7 +845,12 @@ size_t vcb_workspace_bytes(const vcb_problem_t* p) {
   if (p == nullptr || p->Ng <= 0 || p->ld < p->Ng || p->Nc < 0 || p->H < 0 || p->H > VCB_MAX_HARMONICS || p->Hw < 0 ||
       p->Hw > VCB_MAX_HARMONICS)
     return 0;
-  return vcb::make_plan(p, p->U != nullptr).total;
+  size_t n = vcb::make_plan(p, p->U != nullptr).total;
+  if (p->U != nullptr && p->H <= 3 && p->Nb <= 1 && p->Nc > 0) {  // either streaming kernel may serve the call
+    const size_t m = vcb::make_plan_umma(p).total;
+    if (m > n) n = m;
+  }
+  return n;
 }
 
 int vcb_phase_fwd_bwd(const vcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
