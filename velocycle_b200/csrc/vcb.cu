@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "vcb_common.cuh"
@@ -665,7 +666,14 @@ static int run_umma(const vcb_problem_t* p, void* workspace, size_t ws_bytes, vo
   if (e != cudaSuccess) return (int)e;
   {
     umma::Params sp{p->S, p->U, tabF, tabB, omega, zero, p->nu, p->Nb > 0 ? p->dnu : nullptr, p->shape_inv, p->logbeta, p->gamma,
-                    genepart, cellpart, p->Nc, p->Ng, p->ld, pl.Ncp, pl.n_split, p->H, pl.rows};
+                    genepart, cellpart, p->Nc, p->Ng, p->ld, pl.Ncp, pl.n_split, p->H, pl.rows, nullptr,
+                    getenv("VCB_UMMA_DEBUG") ? atoi(getenv("VCB_UMMA_DEBUG")) : 0};
+    static long long* trace_buf = nullptr;  // debug only (VCB_UMMA_TRACE): synchronises and prints
+    if (getenv("VCB_UMMA_TRACE") != nullptr) {
+      if (trace_buf == nullptr) cudaMalloc(&trace_buf, 64 * 8 * sizeof(long long));
+      cudaMemset(trace_buf, 0, 64 * 8 * sizeof(long long));
+      sp.trace = trace_buf;
+    }
     unsigned ev_flags = cudaEventRecordDefault;
     if (p->ev_stream_begin || p->ev_stream_end) {
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -676,6 +684,18 @@ static int run_umma(const vcb_problem_t* p, void* workspace, size_t ws_bytes, vo
     e = vcb_launch_umma_stream(sp, pl.n_tiles, pl.n_split, st);
     if (e != cudaSuccess) return (int)e;
     if (p->ev_stream_end) cudaEventRecordWithFlags((cudaEvent_t)p->ev_stream_end, st, ev_flags);
+    if (sp.trace != nullptr) {
+      static int printed = 0;
+      long long h[64 * 8];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      if (printed++ == 2)
+        for (int c = 0; c < 40; ++c) {
+          printf("chunk %3d:", 64 + c);
+          for (int k = 0; k < 8; ++k) printf(" %7lld", h[c * 8 + k] ? h[c * 8 + k] - h[0] : -1LL);
+          printf("\n");
+        }
+    }
   }
   {
     CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
