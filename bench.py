@@ -319,7 +319,8 @@ def run_ours(a):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "vcb_stream_kernel", "kernel_ms": kern, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                "kernel": ("vcb_umma_stream_kernel (tcgen05, VCB_STREAM_KERNEL=umma)"
+                           if os.environ.get("VCB_STREAM_KERNEL", "").startswith("u") else "vcb_stream_kernel"), "kernel_ms": kern, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                 "note": "latency / issue-slot bound at 16 warps per SM, not HBM bound: every pipe is < 40 % busy (DESIGN.md section 4, profiles/)"}
 
     # ---- e2e: counts start every step in pinned host memory ----------------------------------------------

@@ -52,6 +52,9 @@ extern "C" {
 /* flags */
 #define VCB_FLAG_GRAD 1u          /* also emit every gradient (otherwise log-prob sums only) */
 #define VCB_FLAG_LGAMMA_INLINE 2u /* evaluate lgamma/digamma terms per element instead of via the histogram */
+#define VCB_FLAG_TCGEN05 4u       /* stream with the tcgen05 kernel (vcb_umma.cuh) where it applies: velocity model, VCB_FLAG_GRAD,
+                                     no VCB_FLAG_LGAMMA_INLINE, H <= 3, Nb <= 1; ignored otherwise.  Same results to fp32 rounding;
+                                     the environment variable VCB_STREAM_KERNEL=umma turns it on for every call */
 
 /* error codes (negative) */
 #define VCB_OK 0

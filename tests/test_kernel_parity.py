@@ -26,7 +26,7 @@ def _problem(d, velocity, with_dnu=True):
     return p
 
 
-def _run(d, velocity, with_dnu=True, inline=False, grad=True, perturb=0.3, seed=0, relu_margin=0.05):
+def _run(d, velocity, with_dnu=True, inline=False, grad=True, perturb=0.3, seed=0, relu_margin=0.05, tcgen05=False):
     """``relu_margin``: after perturbing, raise gamma_g so that a = d*omega + gamma >= margin everywhere.
     At the kink of relu(a)+1e-5 an observed kU > 0 makes dL/da = kU/m ~ 1e5*kU, so ANY two fp32 evaluations
     (the reference's own included) differ there by ~1e-7*|d omega|/1e-5 = 1% -- parity to 1e-4 is only defined
@@ -56,6 +56,7 @@ def _run(d, velocity, with_dnu=True, inline=False, grad=True, perturb=0.3, seed=
     out = fused_elbo_grad(
         counts, p["phi"], p["cf"], p["nu"], p.get("dnu"), p["shape_inv"],
         p.get("logbeta"), p.get("gamma"), p.get("nu_omega"), grad=grad, inline_lgamma=inline, want_d_omega=True,
+        tcgen05=tcgen05,
     )
     torch.cuda.synchronize()
     ref = fused_reference(p, dtype=torch.float64, grad=grad)

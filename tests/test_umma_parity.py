@@ -1,0 +1,71 @@
+"""GPU parity of the tcgen05 streaming kernel (VCB_FLAG_TCGEN05, csrc/vcb_umma.cuh) through the C ABI.
+
+Same oracle, same tolerance as test_kernel_parity.py (1e-4 normwise against fp64).  The kernel serves the velocity
+model with gradients, H <= 3 and at most one batch; every other call falls back to the mma.sync kernel, which the
+last test checks.
+"""
+import pytest
+import torch
+
+from test_kernel_parity import _compare, _run
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # Nc, Ng, H, Hw, Nb, Nx
+    (11, 7, 2, 1, 1, 2),        # fewer cells than one 16-cell chunk, one ragged gene tile
+    (16, 256, 3, 1, 1, 1),      # exactly one chunk x one full 256-gene tile
+    (257, 203, 3, 1, 1, 2),     # ragged in both directions: Ng % 4 != 0, Nc % 16 != 0
+    (1849, 76, 1, 0, 1, 1),     # the Appendix-B (Stereo-seq notebook) shape
+    (600, 1918, 1, 1, 1, 1),    # 8 gene tiles, the last one ragged; few chunks per CTA
+    (700, 520, 0, 0, 1, 1),     # H = 0: constant-only basis; 3 gene tiles
+    (5003, 2000, 3, 1, 1, 1),   # BASELINE gene count, CTAs walk more chunks than the accumulator drain period
+    (40000, 300, 2, 2, 1, 3),   # > 32 chunks per CTA: mid-stream drains of the TMEM accumulators, ring wrap-arounds
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("with_dnu", [True, False])
+def test_tcgen05_matches_oracle(shape, with_dnu):
+    from velocycle_b200.synthetic import make_synthetic
+
+    Nc, Ng, H, Hw, Nb, Nx = shape
+    d = make_synthetic(Nc, Ng, H=H, Hw=Hw, Nb=Nb, Nx=Nx, seed=3, device="cuda", sorted_batches=True)
+    out, ref, _ = _run(d, True, with_dnu=with_dnu, tcgen05=True)
+    n = _compare(out, ref)
+    assert n >= (9 if with_dnu else 8)
+
+
+def _both(Nc, Ng, H=3, Hw=1, Nx=1, seed=5):
+    from velocycle_b200.fused import PackedCounts, fused_elbo_grad
+    from velocycle_b200.synthetic import make_synthetic
+
+    d = make_synthetic(Nc, Ng, H=H, Hw=Hw, Nb=1, Nx=Nx, seed=seed, device="cuda", sorted_batches=True)
+    counts = PackedCounts(d.S, d.U, d.Ng, d.batch_id, d.cond_id)
+    args = (counts, d.phi, d.cf, d.nu, d.dnu, d.shape_inv, d.logbeta, torch.exp(d.loggamma), d.nu_omega)
+    a = fused_elbo_grad(*args, grad=True, want_d_omega=True, tcgen05=True)
+    b = fused_elbo_grad(*args, grad=True, want_d_omega=True, tcgen05=True)
+    c = fused_elbo_grad(*args, grad=True, want_d_omega=True, tcgen05=False)
+    torch.cuda.synchronize()
+    return a, b, c
+
+
+def test_tcgen05_is_deterministic_and_agrees_with_the_mma_kernel():
+    a, b, c = _both(3000, 777)
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"{k}: two runs of the tcgen05 kernel differ"
+        ref = c[k].double()
+        err = float((a[k].double() - ref).abs().max() / (ref.abs().max() + 1e-30))
+        assert err <= 2e-5, f"{k}: tcgen05 vs mma.sync kernel {err:.2e}"
+
+
+def test_flag_is_ignored_where_the_kernel_does_not_apply():
+    """Phase model, several batches, H > 3, forward only: VCB_FLAG_TCGEN05 must fall back, not fail."""
+    from velocycle_b200.synthetic import make_synthetic
+
+    for (shape, velocity, grad) in [((300, 130, 3, 1, 1, 1), False, True), ((300, 130, 3, 1, 3, 2), True, True),
+                                    ((300, 130, 4, 1, 1, 1), True, True), ((300, 130, 3, 1, 1, 1), True, False)]:
+        Nc, Ng, H, Hw, Nb, Nx = shape
+        d = make_synthetic(Nc, Ng, H=H, Hw=Hw, Nb=Nb, Nx=Nx, seed=4, device="cuda", sorted_batches=True)
+        out, ref, _ = _run(d, velocity, grad=grad, tcgen05=True)
+        _compare(out, ref)

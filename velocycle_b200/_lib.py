@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libvcb.so")
 
 VCB_FLAG_GRAD = 1
 VCB_FLAG_LGAMMA_INLINE = 2
+VCB_FLAG_TCGEN05 = 4
 VCB_MAX_HARMONICS = 5
 VCB_COUNTS_U8, VCB_COUNTS_U16, VCB_COUNTS_I32 = 1, 2, 4
 

@@ -747,7 +747,7 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
   if (rc != VCB_OK) return rc;
   if (workspace == nullptr) return VCB_ERR_NULL;
   if (((uintptr_t)workspace & 15) != 0) return VCB_ERR_ALIGN;
-  if (stream_kernel_choice() == 1 && umma_applies(p, velo)) return run_umma(p, workspace, ws_bytes, stream);
+  if ((stream_kernel_choice() == 1 || (p->flags & VCB_FLAG_TCGEN05)) && umma_applies(p, velo)) return run_umma(p, workspace, ws_bytes, stream);
   const Plan pl = make_plan(p, velo);
   if (ws_bytes < pl.total) return VCB_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
