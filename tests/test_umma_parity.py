@@ -36,27 +36,31 @@ def test_tcgen05_matches_oracle(shape, with_dnu):
     assert n >= (9 if with_dnu else 8)
 
 
-def _both(Nc, Ng, H=3, Hw=1, Nx=1, seed=5):
-    from velocycle_b200.fused import PackedCounts, fused_elbo_grad
+def _once(tcgen05, Nc=3000, Ng=777):
+    """Same seeded inputs every call (``_run`` perturbs the parameters and keeps a >= 0.05: away from the relu kink, where
+    any two fp32 evaluations differ by per cent -- see test_kernel_parity._run)."""
     from velocycle_b200.synthetic import make_synthetic
 
-    d = make_synthetic(Nc, Ng, H=H, Hw=Hw, Nb=1, Nx=Nx, seed=seed, device="cuda", sorted_batches=True)
-    counts = PackedCounts(d.S, d.U, d.Ng, d.batch_id, d.cond_id)
-    args = (counts, d.phi, d.cf, d.nu, d.dnu, d.shape_inv, d.logbeta, torch.exp(d.loggamma), d.nu_omega)
-    a = fused_elbo_grad(*args, grad=True, want_d_omega=True, tcgen05=True)
-    b = fused_elbo_grad(*args, grad=True, want_d_omega=True, tcgen05=True)
-    c = fused_elbo_grad(*args, grad=True, want_d_omega=True, tcgen05=False)
-    torch.cuda.synchronize()
-    return a, b, c
+    d = make_synthetic(Nc, Ng, H=3, Hw=1, Nb=1, Nx=2, seed=5, device="cuda", sorted_batches=True)
+    out, ref, _ = _run(d, True, tcgen05=tcgen05)
+    return out, ref
 
 
 def test_tcgen05_is_deterministic_and_agrees_with_the_mma_kernel():
-    a, b, c = _both(3000, 777)
+    a, ref = _once(True)
+    b, _ = _once(True)
+    c, _ = _once(False)
     for k in a:
+        if k.startswith("_"):  # scratch buffers (the caller-owned workspace): uninitialised padding may differ
+            continue
         assert torch.equal(a[k], b[k]), f"{k}: two runs of the tcgen05 kernel differ"
-        ref = c[k].double()
-        err = float((a[k].double() - ref).abs().max() / (ref.abs().max() + 1e-30))
-        assert err <= 2e-5, f"{k}: tcgen05 vs mma.sync kernel {err:.2e}"
+        if k not in ref:
+            continue
+        scale = ref[k].abs().max() + 1e-30
+        e_ab = float((a[k].double().cpu().reshape(ref[k].shape) - c[k].double().cpu().reshape(ref[k].shape)).abs().max() / scale)
+        e_c = float((c[k].double().cpu().reshape(ref[k].shape) - ref[k]).abs().max() / scale)
+        # the two kernels differ from each other by no more than either differs from the fp64 truth (+ fp32 noise)
+        assert e_ab <= max(2e-5, 2.0 * e_c), f"{k}: tcgen05 vs mma.sync kernel {e_ab:.2e} (mma.sync vs fp64: {e_c:.2e})"
 
 
 def test_flag_is_ignored_where_the_kernel_does_not_apply():
