@@ -19,6 +19,8 @@
  *                              point widens a compact host staging format (u8 with an overflow list, u16, i32)
  *                              into the float32 cell-major layout the kernels stream, so a count matrix crosses
  *                              PCIe at 1-2 bytes per entry instead of 4-8.
+ *   vcb_csr_to_counts     <->  preprocessing.py:138-143 / 243-249: the sparse anndata layers are scattered into the
+ *                              device layout directly (no dense int64 host copy: 8 B x Nc x Ng of host memory and PCIe).
  *   vcb_clipped_adam      <->  pyro.optim.ClippedAdam.step (pyro/optim/clipped_adam.py), configured in
  *                              tutorials/Tutorial_Capolupo_HumanFibroblasts_OneSample.ipynb cell 27.
  *
@@ -158,6 +160,21 @@ int vcb_count_histogram(const float* M, int64_t Nc, int64_t Ng, int64_t ld, int3
  * and are written after the bulk pass on the same stream.  Exact for every count < 2^24. */
 int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst, const int64_t* over_idx,
                       const float* over_val, int64_t n_over, void* stream);
+
+/* Value types of vcb_csr_to_counts (data_dtype). */
+#define VCB_CSR_F32 0
+#define VCB_CSR_I32 1
+#define VCB_CSR_F64 2
+#define VCB_CSR_I64 3
+
+/* Build the float32 cell-major count matrix dst[Nc][ld] (ld % 4 == 0, ld >= Ng, padding columns zero) on the device from a
+ * CSR matrix of shape (Nc cells, Ng genes) -- the layout of the anndata layers `spliced` / `unspliced` the reference
+ * densifies on the host (preprocessing.py:138-143, 243-249: `.A` / np.array(...) then `torch.tensor(S).to(device)`).
+ * indptr: Nc+1 int64 offsets; indices: int32 gene ids (any order inside a row); data: nnz values of `data_dtype`.
+ * Duplicate (row, gene) entries are summed like scipy's toarray(); entries with a gene id outside [0, Ng) or a negative /
+ * non-integer / >= 2^24 value are skipped and make *status non-zero (status may be NULL).  dst is overwritten. */
+int vcb_csr_to_counts(const int64_t* indptr, const int32_t* indices, const void* data, int32_t data_dtype, int64_t Nc,
+                      int64_t Ng, int64_t ld, float* dst, int32_t* status, void* stream);
 
 /* Multi-tensor ClippedAdam over one flat fp32 buffer of n elements:
  *   lr_t = lr0 * lrd^step (step counts from 1, read from device memory so that graphs replay),

@@ -433,6 +433,32 @@ __global__ void vcb_scatter_overflow_kernel(const long long* __restrict__ idx, c
 // ======================================================================================================
 // Fused multi-tensor ClippedAdam (pyro/optim/clipped_adam.py semantics, lr decayed before use).
 // ======================================================================================================
+// CSR (cells x genes) -> float32 cell-major counts: one warp per cell row, lanes stride over the row's entries.
+// atomicAdd on a zeroed row: duplicates sum like scipy's toarray(), and integer-valued sums are exact and order-independent.
+template <typename T>
+__global__ void __launch_bounds__(256) vcb_csr_to_counts_kernel(const long long* __restrict__ indptr,
+                                                                const int* __restrict__ indices, const T* __restrict__ data,
+                                                                long long Nc, long long Ng, long long ld,
+                                                                float* __restrict__ dst, int* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  bool bad = false;
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < Nc; row += warps) {
+    const long long j0 = indptr[row], j1 = indptr[row + 1];
+    float* out = dst + row * ld;
+    for (long long j = j0 + lane; j < j1; j += 32) {
+      const int g = indices[j];
+      const double v = (double)data[j];
+      if (g < 0 || g >= Ng || !(v >= 0.0) || v >= 16777216.0 || v != floor(v)) {
+        bad = true;
+        continue;
+      }
+      if (v != 0.0) atomicAdd(out + g, (float)v);
+    }
+  }
+  if (bad && status != nullptr) *status = 1;
+}
+
 __global__ void vcb_adam_tick_kernel(long long* step) { *step += 1; }
 
 __global__ void vcb_clipped_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -919,6 +945,34 @@ int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst,
     e = cudaGetLastError();
   }
   return (int)e;
+}
+
+int vcb_csr_to_counts(const int64_t* indptr, const int32_t* indices, const void* data, int32_t data_dtype, int64_t Nc,
+                      int64_t Ng, int64_t ld, float* dst, int32_t* status, void* stream) {
+  if (!indptr || !dst) return VCB_ERR_NULL;
+  if (Nc < 0 || Ng <= 0 || ld < Ng) return VCB_ERR_SIZE;
+  if (ld % 4 != 0 || (((uintptr_t)dst) & 15) != 0) return VCB_ERR_ALIGN;
+  if (Nc == 0) return VCB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)Nc * (size_t)ld * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  if (status) {
+    e = cudaMemsetAsync(status, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (!indices || !data) return VCB_OK;  // an all-zero matrix (nnz = 0) may come without index / value arrays
+  const int bs = 256;
+  long long blocks = (Nc + (bs / 32) - 1) / (bs / 32);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const long long* ip = (const long long*)indptr;
+  switch (data_dtype) {
+    case VCB_CSR_F32: vcb::vcb_csr_to_counts_kernel<float><<<(unsigned)blocks, bs, 0, st>>>(ip, indices, (const float*)data, Nc, Ng, ld, dst, status); break;
+    case VCB_CSR_I32: vcb::vcb_csr_to_counts_kernel<int><<<(unsigned)blocks, bs, 0, st>>>(ip, indices, (const int*)data, Nc, Ng, ld, dst, status); break;
+    case VCB_CSR_F64: vcb::vcb_csr_to_counts_kernel<double><<<(unsigned)blocks, bs, 0, st>>>(ip, indices, (const double*)data, Nc, Ng, ld, dst, status); break;
+    case VCB_CSR_I64: vcb::vcb_csr_to_counts_kernel<long long><<<(unsigned)blocks, bs, 0, st>>>(ip, indices, (const long long*)data, Nc, Ng, ld, dst, status); break;
+    default: return VCB_ERR_SIZE;
+  }
+  return (int)cudaGetLastError();
 }
 
 int vcb_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_dev,

@@ -238,6 +238,40 @@ class PackedCounts:
         return out
 
     @staticmethod
+    def pack_csr(M, device) -> torch.Tensor:
+        """(Nc cells, Ng genes) scipy.sparse matrix -> the same (Nc, roundup(Ng,4)) float32 device matrix as ``pack_matrix``,
+        built ON the device by ``vcb_csr_to_counts`` from the three CSR arrays: the dense int64 host copy the reference
+        makes (``preprocessing.py:138-143, 243-249``: 8 bytes x Nc x Ng of host memory and PCIe) never exists."""
+        import numpy as np
+
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.VcbError("pack_csr builds the count matrix on a CUDA device (there is no CPU path)")
+        lib = _lib.load()
+        csr = M.tocsr()
+        Nc, Ng = csr.shape
+        ld = (Ng + 3) // 4 * 4
+        out = torch.empty((Nc, ld), dtype=torch.float32, device=device)
+        if Nc == 0:
+            return out
+        kinds = {np.dtype(np.float32): _lib.VCB_CSR_F32, np.dtype(np.int32): _lib.VCB_CSR_I32,
+                 np.dtype(np.float64): _lib.VCB_CSR_F64, np.dtype(np.int64): _lib.VCB_CSR_I64}
+        data = csr.data
+        if data.dtype not in kinds:
+            data = data.astype(np.float64 if data.dtype.kind == "f" else np.int64)
+        indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(device, non_blocking=True)
+        nnz = int(csr.indptr[-1])
+        indices = torch.from_numpy(np.ascontiguousarray(csr.indices[:nnz], dtype=np.int32)).to(device) if nnz else None
+        values = torch.from_numpy(np.ascontiguousarray(data[:nnz])).to(device) if nnz else None
+        status = torch.zeros(1, dtype=torch.int32, device=device)
+        rc = lib.vcb_csr_to_counts(indptr.data_ptr(), _ptr(indices), _ptr(values), kinds[np.dtype(data.dtype)], Nc, Ng, ld,
+                                   out.data_ptr(), status.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "vcb_csr_to_counts")
+        if int(status.item()) != 0:
+            raise _lib.VcbError("the sparse count matrix holds gene ids outside [0, Ng) or values that are not integers in [0, 2^24)")
+        return out
+
+    @staticmethod
     def one_hot_to_ids(D: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         """mp.Db (Nb,1,Nc) / (Nb,1,1,1,Nc) or mp.D (Nx,1,1,Nc) one-hot -> int32 ids (Nc,)."""
         if D is None:

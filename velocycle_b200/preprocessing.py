@@ -54,8 +54,25 @@ def count_factor_from_totals(S_totals: torch.Tensor) -> torch.Tensor:
     return torch.log(t / t.mean())
 
 
-def _pack(S_cells_by_genes: torch.Tensor, device) -> torch.Tensor:
-    return PackedCounts.pack_matrix(S_cells_by_genes.to(device), layout="cells_by_genes")
+def _is_sparse(M) -> bool:
+    return hasattr(M, "tocsr") and not isinstance(M, torch.Tensor)
+
+
+def _pack(S_cells_by_genes, device) -> torch.Tensor:
+    """(Nc, Ng) counts -> the packed float32 device matrix.  A scipy.sparse matrix (the anndata layers) goes to a CUDA device
+    as CSR and is scattered there (``PackedCounts.pack_csr``); dense input is copied and widened."""
+    if _is_sparse(S_cells_by_genes):
+        if torch.device(device).type == "cuda":
+            return PackedCounts.pack_csr(S_cells_by_genes, device)
+        S_cells_by_genes = torch.as_tensor(S_cells_by_genes.toarray())
+    return PackedCounts.pack_matrix(torch.as_tensor(S_cells_by_genes).to(device), layout="cells_by_genes")
+
+
+def _counts_layer(layer):
+    """An anndata layer as the builders take it: sparse stays sparse (no dense host copy), anything else becomes int64."""
+    if _is_sparse(layer):
+        return layer
+    return torch.as_tensor(np.asarray(layer).astype(np.int64))
 
 
 def make_phase_metaparams(
@@ -166,8 +183,8 @@ def preprocess_for_phase_estimation(
         raise ValueError(f"{gene_selection_model=} is not a valid model")
     if noisemodel != "NegativeBinomial" or normalize:
         raise ValueError("the B200 path implements the NegativeBinomial noise model on raw integer counts")
-    S = torch.as_tensor(_dense(anndata.layers["spliced"]).astype(np.int64))
-    U = torch.as_tensor(_dense(anndata.layers["unspliced"]).astype(np.int64))
+    S = _counts_layer(anndata.layers["spliced"])
+    U = _counts_layer(anndata.layers["unspliced"])
     return make_phase_metaparams(
         S, U, cycle_obj.means_tensor.T, cycle_obj.stds_tensor.T, phase_obj.phi_xy_tensor.T,
         batch_id=_ids_from_design(design_mtx), Nb=int(np.asarray(design_mtx).shape[-1]), n_harmonics=n_harmonics,
@@ -192,8 +209,8 @@ def preprocess_for_velocity_estimation(
         raise ValueError(f"{gene_selection_model=} is not a valid model")
     if noisemodel != "NegativeBinomial" or normalize:
         raise ValueError("the B200 path implements the NegativeBinomial noise model on raw integer counts")
-    S = torch.as_tensor(_dense(anndata.layers["spliced"]).astype(np.int64))
-    U = torch.as_tensor(_dense(anndata.layers["unspliced"]).astype(np.int64))
+    S = _counts_layer(anndata.layers["spliced"])
+    U = _counts_layer(anndata.layers["unspliced"])
     cf = count_factor if isinstance(count_factor, torch.Tensor) else None
     return make_velocity_metaparams(
         S, U, cycle_obj.means_tensor.T, cycle_obj.stds_tensor.T, phase_obj.phi_xy_tensor.T,
