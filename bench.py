@@ -331,11 +331,12 @@ def run_ours(a):
 
             from velocycle_b200.fused import HostCounts
 
-            # The step's inputs start in pinned host memory in the narrowest exact integer format (HostCounts: one
-            # byte per count, escapes as an (index, value) list); each e2e step copies them to the device, widens
-            # them into the float32 [Nc][ld] matrices (vcb_expand_counts) and runs the SVI step on them.
-            hS = HostCounts.from_tensor(counts.S)
-            hU = HostCounts.from_tensor(counts.U)
+            # The step's inputs start in pinned host memory in the narrowest exact integer format (HostCounts: 2- or 4-bit
+            # codes with an escape byte stream, or one byte per count; large counts as an (index, value) list); each e2e
+            # step copies them to the device, widens them into the float32 [Nc][ld] matrices (vcb_expand_counts[_packed])
+            # and runs the SVI step on them.
+            hS = HostCounts.from_tensor(counts.S, sub_byte=True)
+            hU = HostCounts.from_tensor(counts.U, sub_byte=True)
             h2d = hS.nbytes + hU.nbytes
             need = h2d
             avail = psutil.virtual_memory().available
@@ -359,13 +360,14 @@ def run_ours(a):
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item()) / n_e2e
-            fmt_name = {1: "u8 + overflow list", 2: "u16", 4: "i32"}
+            fmt_name = {1: "u8 + overflow list", 2: "u16", 4: "i32", 16: "2-bit codes + escape bytes + overflow list",
+                        32: "4-bit codes + escape bytes + overflow list"}
             e2e = {"value": Nc * world * Ng / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": n_e2e,
                    "note": ("both count matrices copied from pinned host memory every step in the staging format of "
                             f"velocycle_b200.fused.HostCounts (S: {fmt_name[hS.fmt]}, U: {fmt_name[hU.fmt]}; "
                             f"{(0 if hS.over_idx is None else hS.over_idx.numel()) + (0 if hU.over_idx is None else hU.over_idx.numel())}"
-                            " escaped entries), widened on the device to the float32 layout by vcb_expand_counts, "
+                            " entries in the overflow lists), widened on the device to the float32 layout by vcb_expand_counts[_packed], "
                             "then one GraphedSVI step with the loss read back")}
             del hS, hU
         except Exception as exc:  # pragma: no cover

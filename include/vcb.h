@@ -161,6 +161,16 @@ int vcb_count_histogram(const float* M, int64_t Nc, int64_t Ng, int64_t ld, int3
 int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst, const int64_t* over_idx,
                       const float* over_val, int64_t n_over, void* stream);
 
+/* Sub-byte staging (vcb_expand_counts_packed): `bits` = 2 or 4 bits per entry, 32/bits entries per little-endian 32-bit
+ * word (entry i of a word in bits [i*bits, (i+1)*bits)).  The all-ones code is an escape: the entry's value is the next byte
+ * of `side` in entry order; a side byte of 255 is itself an escape into the (over_idx, over_val) list, exactly as in
+ * vcb_expand_counts.  `block_off[j]` = number of escapes before word 256*j (one entry per VCB_PACKED_BLOCK_WORDS words), so
+ * that blocks decode independently.  `codes` holds a whole number of blocks (zero padded); n = Nc*ld entries are written.
+ * Typical scRNA-seq counts cost 0.3-0.55 bytes per entry instead of 1 (u8) or 8 (the reference's int64 upload). */
+#define VCB_PACKED_BLOCK_WORDS 256
+int vcb_expand_counts_packed(const uint32_t* codes, int32_t bits, const uint8_t* side, const int64_t* block_off, int64_t n,
+                             float* dst, const int64_t* over_idx, const float* over_val, int64_t n_over, void* stream);
+
 /* Value types of vcb_csr_to_counts (data_dtype). */
 #define VCB_CSR_F32 0
 #define VCB_CSR_I32 1

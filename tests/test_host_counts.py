@@ -107,3 +107,66 @@ def test_expand_counts_argument_errors():
     assert lib.vcb_expand_counts(t.data_ptr(), 3, 16, t.data_ptr(), None, None, 0, None) == -2
     assert lib.vcb_expand_counts(t.data_ptr() + 4, 1, 16, t.data_ptr(), None, None, 0, None) == -3
     assert lib.vcb_expand_counts(t.data_ptr(), 2, 16, t.data_ptr(), None, None, 5, None) == -1  # overflow list only with u8
+
+
+# ---- sub-byte staging (2 / 4 bits per entry + escape side stream; vcb_expand_counts_packed) -------------------------------
+def _decode_sub_byte(h):
+    """Pure-torch restatement of the format (include/vcb.h) -- the oracle of the device decoder."""
+    bits = h.bits
+    per, E = 32 // bits, (1 << bits) - 1
+    n = h.shape[0] * h.shape[1]
+    w = h.staged.to(torch.int64) & 0xFFFFFFFF
+    codes = ((w[:, None] >> (torch.arange(per) * bits)) & E).reshape(-1)
+    cnt = (codes == E).reshape(-1, per * _lib.VCB_PACKED_BLOCK_WORDS).sum(1)
+    assert torch.equal(h.block_off, torch.cumsum(cnt, 0) - cnt)       # escapes before each block
+    out = codes[:n].clone().float()
+    esc = (out == E).nonzero().reshape(-1)
+    out[esc] = h.side[: esc.numel()].float()                             # escape bytes in entry order
+    if h.over_idx is not None:
+        out[h.over_idx] = h.over_val                                     # side byte 255 -> overflow list
+    return out.reshape(h.shape)
+
+
+def _sparse_matrix(lam, Nc, ld, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    M = torch.poisson(torch.full((Nc, ld), lam), generator=g)
+    if Nc > 6 and ld > 6:
+        M[3, 5], M[0, 0], M[5, 1], M[Nc - 1, ld - 1] = 255.0, 70000.0, 254.0, 16.0
+    return M
+
+
+@pytest.mark.parametrize("lam,shape,fmt", [(0.4, (3000, 2000), _lib.VCB_COUNTS_B2), (2.0, (777, 52), _lib.VCB_COUNTS_B4),
+                                           (3.7, (4100, 200), _lib.VCB_COUNTS_B4), (400.0, (300, 40), _lib.VCB_COUNTS_I32)])
+def test_sub_byte_format_choice_and_host_packing(lam, shape, fmt):
+    M = _sparse_matrix(lam, *shape)
+    h = HostCounts.from_tensor(M, sub_byte=True)
+    assert h.fmt == fmt
+    if fmt in (_lib.VCB_COUNTS_B2, _lib.VCB_COUNTS_B4):
+        assert torch.equal(_decode_sub_byte(h), M)
+        assert h.nbytes < 0.62 * M.numel() + 8192        # well under one byte per entry
+    assert HostCounts.from_tensor(M).fmt in (_lib.VCB_COUNTS_U8, _lib.VCB_COUNTS_U16, _lib.VCB_COUNTS_I32)   # opt-in only
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lam", [0.4, 2.0, 3.7])
+@pytest.mark.parametrize("shape", [(777, 52), (1, 4), (4099, 2000), (70000, 100)])
+def test_sub_byte_device_round_trip_is_bit_exact(lam, shape):
+    M = _sparse_matrix(lam, *shape, seed=5)
+    for src in (M, M.cuda()):                              # packed from a host or a device-resident matrix
+        h = HostCounts.from_tensor(src, sub_byte=True)
+        dst = torch.full(M.shape, -1.0, device="cuda")
+        h.upload(dst)
+        h.upload(dst)
+        torch.cuda.synchronize()
+        assert torch.equal(dst.cpu(), M), (h.fmt, shape)
+
+
+@pytest.mark.gpu
+def test_expand_counts_packed_argument_errors():
+    lib = _lib.load()
+    t = torch.zeros(4096, device="cuda")
+    o = torch.zeros(8, dtype=torch.int64, device="cuda")
+    assert lib.vcb_expand_counts_packed(None, 4, t.data_ptr(), o.data_ptr(), 16, t.data_ptr(), None, None, 0, None) == -1
+    assert lib.vcb_expand_counts_packed(t.data_ptr(), 3, t.data_ptr(), o.data_ptr(), 16, t.data_ptr(), None, None, 0, None) == -2
+    assert lib.vcb_expand_counts_packed(t.data_ptr(), 4, t.data_ptr(), o.data_ptr(), 16, t.data_ptr() + 4, None, None, 0, None) == -3
+    assert lib.vcb_expand_counts_packed(t.data_ptr(), 2, t.data_ptr(), o.data_ptr(), 16, t.data_ptr(), None, None, 3, None) == -1

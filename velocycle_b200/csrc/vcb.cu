@@ -424,6 +424,55 @@ __global__ void __launch_bounds__(256) vcb_expand_counts_kernel(const T* __restr
     dst[i] = count_to_float(src[i]);
 }
 
+// Sub-byte staging -> float32 (format: include/vcb.h).  One thread per 32-bit code word, one CTA per 256-word block; the
+// escapes of a block are located with a block-wide exclusive scan of the per-word escape counts.
+template <int BITS>
+__global__ void __launch_bounds__(VCB_PACKED_BLOCK_WORDS) vcb_expand_packed_kernel(const uint32_t* __restrict__ codes,
+                                                                                  const uint8_t* __restrict__ side,
+                                                                                  const long long* __restrict__ block_off,
+                                                                                  long long n, long long n_blocks,
+                                                                                  float* __restrict__ dst) {
+  constexpr int PER = 32 / BITS;
+  constexpr uint32_t E = (1u << BITS) - 1u;
+  __shared__ int s_warp[VCB_PACKED_BLOCK_WORDS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const long long w = blk * VCB_PACKED_BLOCK_WORDS + threadIdx.x;
+    const uint32_t word = __ldcs(codes + w);
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) cnt += (((word >> (k * BITS)) & E) == E) ? 1 : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int i = 0; i < warp; ++i) before += s_warp[i];
+    long long pos = block_off[blk] + before + (incl - cnt);
+    float v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const uint32_t c = (word >> (k * BITS)) & E;
+      v[k] = (float)c;
+      if (c == E) v[k] = (float)side[pos++];
+    }
+    const long long e0 = w * PER;
+    if (e0 + PER <= n) {
+      float4* d4 = reinterpret_cast<float4*>(dst + e0);
+#pragma unroll
+      for (int j = 0; j < PER / 4; ++j) __stcs(d4 + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+    } else {
+      for (int k = 0; k < PER; ++k)
+        if (e0 + k < n) dst[e0 + k] = v[k];
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void vcb_scatter_overflow_kernel(const long long* __restrict__ idx, const float* __restrict__ val,
                                             long long n, float* __restrict__ dst) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -941,6 +990,33 @@ int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst,
   if (n_over > 0) {
     long long b = (n_over + bs - 1) / bs;
     if (b > blocks) b = blocks;
+    vcb::vcb_scatter_overflow_kernel<<<(unsigned)b, bs, 0, st>>>((const long long*)over_idx, over_val, n_over, dst);
+    e = cudaGetLastError();
+  }
+  return (int)e;
+}
+
+int vcb_expand_counts_packed(const uint32_t* codes, int32_t bits, const uint8_t* side, const int64_t* block_off, int64_t n,
+                             float* dst, const int64_t* over_idx, const float* over_val, int64_t n_over, void* stream) {
+  if (!codes || !block_off || !dst) return VCB_ERR_NULL;
+  if (n < 0 || n_over < 0 || (bits != 2 && bits != 4)) return VCB_ERR_SIZE;
+  if (n_over > 0 && (!over_idx || !over_val)) return VCB_ERR_NULL;
+  if ((((uintptr_t)codes) & 3) != 0 || (((uintptr_t)dst) & 15) != 0) return VCB_ERR_ALIGN;
+  if (n == 0) return VCB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long per_block = (long long)VCB_PACKED_BLOCK_WORDS * (32 / bits);
+  const long long n_blocks = (n + per_block - 1) / per_block;
+  long long grid = n_blocks < 148LL * 16 ? n_blocks : 148LL * 16;
+  if (bits == 2)
+    vcb::vcb_expand_packed_kernel<2><<<(unsigned)grid, VCB_PACKED_BLOCK_WORDS, 0, st>>>(codes, side, (const long long*)block_off, n, n_blocks, dst);
+  else
+    vcb::vcb_expand_packed_kernel<4><<<(unsigned)grid, VCB_PACKED_BLOCK_WORDS, 0, st>>>(codes, side, (const long long*)block_off, n, n_blocks, dst);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (n_over > 0) {
+    const int bs = 256;
+    long long b = (n_over + bs - 1) / bs;
+    if (b > 148 * 8) b = 148 * 8;
     vcb::vcb_scatter_overflow_kernel<<<(unsigned)b, bs, 0, st>>>((const long long*)over_idx, over_val, n_over, dst);
     e = cudaGetLastError();
   }

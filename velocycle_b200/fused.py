@@ -102,9 +102,10 @@ class HostCounts:
 
     ESCAPE = 255
 
-    def __init__(self, staged: torch.Tensor, fmt: int, shape, over_idx=None, over_val=None):
+    def __init__(self, staged: torch.Tensor, fmt: int, shape, over_idx=None, over_val=None, side=None, block_off=None):
         self.staged, self.fmt, self.shape = staged, fmt, tuple(shape)
         self.over_idx, self.over_val = over_idx, over_val
+        self.side, self.block_off = side, block_off  # sub-byte formats: escape bytes in entry order, escapes before each block
         self._dev = None  # device staging buffers, created on first upload
 
     @property
@@ -113,7 +114,15 @@ class HostCounts:
         n = self.staged.numel() * self.staged.element_size()
         if self.over_idx is not None:
             n += self.over_idx.numel() * 8 + self.over_val.numel() * 4
+        if self.side is not None:
+            n += self.side.numel() + self.block_off.numel() * 8
         return n
+
+    @property
+    def bits(self) -> int:
+        """Bits per entry of the main stream."""
+        return {_lib.VCB_COUNTS_B2: 2, _lib.VCB_COUNTS_B4: 4, _lib.VCB_COUNTS_U8: 8, _lib.VCB_COUNTS_U16: 16,
+                _lib.VCB_COUNTS_I32: 32}[self.fmt]
 
     @staticmethod
     def choose_format(max_count: float, escape_fraction: float) -> int:
@@ -124,16 +133,30 @@ class HostCounts:
         return _lib.VCB_COUNTS_U16 if max_count < 2 ** 16 else _lib.VCB_COUNTS_I32
 
     @classmethod
-    def from_tensor(cls, M: torch.Tensor, chunk_rows: int = 1 << 16) -> "HostCounts":
+    def from_tensor(cls, M: torch.Tensor, chunk_rows: int = 1 << 16, sub_byte: bool = False) -> "HostCounts":
         """``M``: (Nc, ld) non-negative integer-valued matrix (any real dtype, CPU or CUDA), already padded to the
-        device pitch.  Packed chunk by chunk on the device the data lives on; the staging copy is pinned."""
+        device pitch.  Packed chunk by chunk on the device the data lives on; the staging copy is pinned.
+        ``sub_byte``: also consider the 2- and 4-bit formats (escape bytes in a side stream) and take the smallest."""
         assert M.dim() == 2
         Nc, ld = M.shape
         mx = float(M.max()) if M.numel() else 0.0
-        n_esc = 0
+        n_esc = n3 = n15 = 0
         for r0 in range(0, Nc, chunk_rows):
-            n_esc += int((M[r0: r0 + chunk_rows] >= cls.ESCAPE).sum())
+            blk = M[r0: r0 + chunk_rows]
+            n_esc += int((blk >= cls.ESCAPE).sum())
+            if sub_byte:
+                n3 += int((blk >= 3).sum())
+                n15 += int((blk >= 15).sum())
         fmt = cls.choose_format(mx, n_esc / max(1, M.numel()))
+        if sub_byte and M.numel() and ld % 4 == 0 and mx < 2 ** 24:
+            n = M.numel()
+            over = 12 * n_esc  # counts >= 255 travel as (int64 index, float32 value) pairs in every byte / sub-byte format
+            size = {_lib.VCB_COUNTS_B2: n / 4 + n3 + over, _lib.VCB_COUNTS_B4: n / 2 + n15 + over,
+                    fmt: n * {_lib.VCB_COUNTS_U8: 1, _lib.VCB_COUNTS_U16: 2, _lib.VCB_COUNTS_I32: 4}[fmt]
+                    + (over if fmt == _lib.VCB_COUNTS_U8 else 0)}
+            best = min(size, key=size.get)
+            if best in (_lib.VCB_COUNTS_B2, _lib.VCB_COUNTS_B4):
+                return cls._pack_sub_byte(M, 2 if best == _lib.VCB_COUNTS_B2 else 4, best, n_esc)
         tdt = {_lib.VCB_COUNTS_U8: torch.uint8, _lib.VCB_COUNTS_U16: torch.uint16, _lib.VCB_COUNTS_I32: torch.int32}[fmt]
         pin = torch.cuda.is_available()
         staged = torch.empty((Nc, ld), dtype=tdt, pin_memory=pin)
@@ -159,6 +182,53 @@ class HostCounts:
                 over_idx, over_val = over_idx.pin_memory(), over_val.pin_memory()
         return cls(staged, fmt, (Nc, ld), over_idx, over_val)
 
+    @classmethod
+    def _pack_sub_byte(cls, M: torch.Tensor, bits: int, fmt: int, n_over: int) -> "HostCounts":
+        """2- or 4-bit codes, 32/bits per little-endian int32 word; code 2^bits-1 = escape -> next byte of the side stream;
+        side byte 255 -> (index, value) overflow list (format: include/vcb.h, vcb_expand_counts_packed)."""
+        Nc, ld = M.shape
+        n = Nc * ld
+        per, E = 32 // bits, (1 << bits) - 1
+        per_block = per * _lib.VCB_PACKED_BLOCK_WORDS
+        n_blocks = (n + per_block - 1) // per_block
+        pin = torch.cuda.is_available()
+        codes = torch.zeros(n_blocks * _lib.VCB_PACKED_BLOCK_WORDS, dtype=torch.int32, pin_memory=pin)
+        esc_per_block = torch.zeros(n_blocks, dtype=torch.int64)
+        rows = max(1024, (1 << 16) // 1024 * 1024)  # rows * ld is a whole number of blocks (ld % 4 == 0)
+        shifts = (torch.arange(per, dtype=torch.int64) * bits)
+        side, idx, val = [], [], []
+        for r0 in range(0, Nc, rows):
+            flat = M[r0: r0 + rows].reshape(-1)
+            e0 = r0 * ld
+            pad = (-flat.numel()) % per_block
+            if pad:
+                flat = torch.cat([flat, flat.new_zeros(pad)])
+            esc = flat >= E
+            side.append(flat[esc].clamp(max=cls.ESCAPE).to(torch.uint8).cpu())
+            if n_over:
+                nz = (flat >= cls.ESCAPE).nonzero().reshape(-1)
+                idx.append((nz + e0).to(torch.int64).cpu())
+                val.append(flat[nz].to(torch.float32).cpu())
+            c = flat.clamp(max=E).to(torch.int64).reshape(-1, per)
+            words = (c << shifts.to(c.device)).sum(1)
+            words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+            w0 = e0 // per
+            codes[w0: w0 + words.numel()].copy_(words)
+            b0 = e0 // per_block
+            cnt = esc.reshape(-1, per_block).sum(1).to(torch.int64).cpu()
+            esc_per_block[b0: b0 + cnt.numel()] = cnt
+        side = torch.cat(side) if side else torch.zeros(0, dtype=torch.uint8)
+        if side.numel() == 0:
+            side = torch.zeros(1, dtype=torch.uint8)  # (a valid pointer for the kernel)
+        block_off = torch.cumsum(esc_per_block, 0) - esc_per_block
+        over_idx = torch.cat(idx) if n_over else None
+        over_val = torch.cat(val) if n_over else None
+        if pin:
+            side, block_off = side.pin_memory(), block_off.pin_memory()
+            if n_over:
+                over_idx, over_val = over_idx.pin_memory(), over_val.pin_memory()
+        return cls(codes, fmt, (Nc, ld), over_idx, over_val, side=side, block_off=block_off)
+
     def upload(self, dst: torch.Tensor) -> None:
         """H2D copy of the staging buffer + widening into ``dst`` (float32 CUDA (Nc, ld), contiguous), all on the
         current stream; nothing synchronises."""
@@ -181,6 +251,16 @@ class HostCounts:
             d_v.copy_(self.over_val, non_blocking=True)
             n_over = d_i.numel()
         lib = _lib.load()
+        if self.side is not None:
+            if getattr(self, "_dev_side", None) is None or self._dev_side[0].device != dev:
+                self._dev_side = (torch.empty_like(self.side, device=dev), torch.empty_like(self.block_off, device=dev))
+            d_side, d_off = self._dev_side
+            d_side.copy_(self.side, non_blocking=True)
+            d_off.copy_(self.block_off, non_blocking=True)
+            _lib.check(lib.vcb_expand_counts_packed(d_st.data_ptr(), self.bits, d_side.data_ptr(), d_off.data_ptr(), dst.numel(),
+                                                    dst.data_ptr(), _ptr(d_i), _ptr(d_v), n_over,
+                                                    torch.cuda.current_stream(dev).cuda_stream), "vcb_expand_counts_packed")
+            return
         _lib.check(lib.vcb_expand_counts(d_st.data_ptr(), self.fmt, dst.numel(), dst.data_ptr(), _ptr(d_i), _ptr(d_v),
                                          n_over, torch.cuda.current_stream(dev).cuda_stream), "vcb_expand_counts")
 
