@@ -344,16 +344,26 @@ def run_ours(a):
                 raise MemoryError(f"{need * world} B of pinned host staging do not fit in {avail} B of host RAM")
             S_check = counts.S[:4096].clone()
             n_e2e = max(2, min(a.steps, 10))
-            def e2e_step():
-                hS.upload(counts.S)
-                hU.upload(counts.U)
-                return svi_step()
-            e2e_step()
+            # Every step's inputs cross PCIe inside the timed region.  The copies run on a second stream into the spare
+            # set of device staging buffers (HostCounts.start_upload), so the copy of step i+1 overlaps the SVI step i --
+            # what any input pipeline does; the first copy of the region is not overlapped with anything.
+            copy_stream = torch.cuda.Stream(device=dev)
+            def start_copies():
+                hS.start_upload(dev, copy_stream)
+                hU.start_upload(dev, copy_stream)
+            def e2e_steps(k):
+                start_copies()
+                for i in range(k):
+                    hS.finish_upload(counts.S)
+                    hU.finish_upload(counts.U)
+                    if i + 1 < k:
+                        start_copies()
+                    svi_step()
+            e2e_steps(2)
             assert torch.equal(S_check, counts.S[:4096]), "HostCounts round trip changed the counts"
             barrier()
             e0.record()
-            for _ in range(n_e2e):
-                e2e_step()
+            e2e_steps(n_e2e)
             e1.record()
             barrier()
             t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -368,7 +378,7 @@ def run_ours(a):
                             f"velocycle_b200.fused.HostCounts (S: {fmt_name[hS.fmt]}, U: {fmt_name[hU.fmt]}; "
                             f"{(0 if hS.over_idx is None else hS.over_idx.numel()) + (0 if hU.over_idx is None else hU.over_idx.numel())}"
                             " entries in the overflow lists), widened on the device to the float32 layout by vcb_expand_counts[_packed], "
-                            "then one GraphedSVI step with the loss read back")}
+                            "then one GraphedSVI step with the loss read back; the copies of step i+1 run on a copy stream under step i")}
             del hS, hU
         except Exception as exc:  # pragma: no cover
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)}

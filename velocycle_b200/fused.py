@@ -229,40 +229,72 @@ class HostCounts:
                 over_idx, over_val = over_idx.pin_memory(), over_val.pin_memory()
         return cls(codes, fmt, (Nc, ld), over_idx, over_val, side=side, block_off=block_off)
 
-    def upload(self, dst: torch.Tensor) -> None:
-        """H2D copy of the staging buffer + widening into ``dst`` (float32 CUDA (Nc, ld), contiguous), all on the
-        current stream; nothing synchronises."""
+    # ---- device side: two sets of staging buffers, so that the H2D copy of the next upload overlaps the work on the last one
+    def _device_set(self, dev, k: int):
+        if self._dev is None or self._dev[0][0].device != dev:
+            def mk(t):
+                return None if t is None else torch.empty_like(t, device=dev)
+            self._dev = [[mk(self.staged), mk(self.over_idx), mk(self.over_val), mk(self.side), mk(self.block_off), None]
+                         for _ in range(2)]
+            self._next, self._pending = 0, None
+        return self._dev[k]
+
+    def start_upload(self, device, stream: Optional["torch.cuda.Stream"] = None) -> None:
+        """Enqueue the H2D copies of the staging buffers on ``stream`` (default: the current stream) into the spare device
+        buffer set.  With a dedicated copy stream they overlap whatever the compute stream is doing (the previous SVI step);
+        ``finish_upload`` makes the compute stream wait for them.  Nothing synchronises the host."""
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.VcbError("HostCounts uploads need a CUDA device: velocycle_b200 has no CPU path")
+        k = getattr(self, "_next", 0)
+        bufs = self._device_set(dev, k)
+        k = self._next
+        bufs = self._dev[k]
+        stream = stream or torch.cuda.current_stream(dev)
+        if bufs[5] is not None:
+            stream.wait_event(bufs[5])  # the widening kernel that last read this set has finished
+        with torch.cuda.stream(stream):
+            for d, h in zip(bufs[:5], (self.staged, self.over_idx, self.over_val, self.side, self.block_off)):
+                if d is not None:
+                    d.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._pending = (k, ev)
+        self._next = 1 - k
+
+    def finish_upload(self, dst: torch.Tensor) -> None:
+        """Current stream: wait for the copies of the last ``start_upload``, widen them into ``dst`` (float32 CUDA (Nc, ld))."""
         if not dst.is_cuda:
             raise _lib.VcbError("HostCounts.upload needs a CUDA destination: velocycle_b200 has no CPU path")
         assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape) == self.shape
+        if getattr(self, "_pending", None) is None:
+            raise _lib.VcbError("finish_upload without start_upload")
         dev = dst.device
-        if self._dev is None or self._dev[0].device != dev:
-            d_st = torch.empty(self.staged.shape, dtype=self.staged.dtype, device=dev)
-            d_i = d_v = None
-            if self.over_idx is not None:
-                d_i = torch.empty_like(self.over_idx, device=dev)
-                d_v = torch.empty_like(self.over_val, device=dev)
-            self._dev = (d_st, d_i, d_v)
-        d_st, d_i, d_v = self._dev
-        d_st.copy_(self.staged, non_blocking=True)
-        n_over = 0
-        if d_i is not None:
-            d_i.copy_(self.over_idx, non_blocking=True)
-            d_v.copy_(self.over_val, non_blocking=True)
-            n_over = d_i.numel()
+        k, ev = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev)
+        d_st, d_i, d_v, d_side, d_off, _ = self._dev[k]
+        n_over = 0 if d_i is None else d_i.numel()
         lib = _lib.load()
-        if self.side is not None:
-            if getattr(self, "_dev_side", None) is None or self._dev_side[0].device != dev:
-                self._dev_side = (torch.empty_like(self.side, device=dev), torch.empty_like(self.block_off, device=dev))
-            d_side, d_off = self._dev_side
-            d_side.copy_(self.side, non_blocking=True)
-            d_off.copy_(self.block_off, non_blocking=True)
+        if d_side is not None:
             _lib.check(lib.vcb_expand_counts_packed(d_st.data_ptr(), self.bits, d_side.data_ptr(), d_off.data_ptr(), dst.numel(),
-                                                    dst.data_ptr(), _ptr(d_i), _ptr(d_v), n_over,
-                                                    torch.cuda.current_stream(dev).cuda_stream), "vcb_expand_counts_packed")
-            return
-        _lib.check(lib.vcb_expand_counts(d_st.data_ptr(), self.fmt, dst.numel(), dst.data_ptr(), _ptr(d_i), _ptr(d_v),
-                                         n_over, torch.cuda.current_stream(dev).cuda_stream), "vcb_expand_counts")
+                                                    dst.data_ptr(), _ptr(d_i), _ptr(d_v), n_over, cur.cuda_stream),
+                       "vcb_expand_counts_packed")
+        else:
+            _lib.check(lib.vcb_expand_counts(d_st.data_ptr(), self.fmt, dst.numel(), dst.data_ptr(), _ptr(d_i), _ptr(d_v),
+                                             n_over, cur.cuda_stream), "vcb_expand_counts")
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._dev[k][5] = done
+
+    def upload(self, dst: torch.Tensor) -> None:
+        """H2D copy of the staging buffers + widening into ``dst`` (float32 CUDA (Nc, ld), contiguous), all on the
+        current stream; nothing synchronises."""
+        if not dst.is_cuda:
+            raise _lib.VcbError("HostCounts.upload needs a CUDA destination: velocycle_b200 has no CPU path")
+        self.start_upload(dst.device)
+        self.finish_upload(dst)
 
 
 class PackedCounts:
