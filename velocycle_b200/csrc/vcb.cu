@@ -742,13 +742,18 @@ static int run_umma(const vcb_problem_t* p, void* workspace, size_t ws_bytes, vo
   {
     umma::Params sp{p->S, p->U, tabF, tabB, omega, zero, p->nu, p->Nb > 0 ? p->dnu : nullptr, p->shape_inv, p->logbeta, p->gamma,
                     genepart, cellpart, p->Nc, p->Ng, p->ld, pl.Ncp, pl.n_split, p->H, pl.rows, nullptr,
-                    getenv("VCB_UMMA_DEBUG") ? atoi(getenv("VCB_UMMA_DEBUG")) : 0};
-    static long long* trace_buf = nullptr;  // debug only (VCB_UMMA_TRACE): synchronises and prints
+                    0};
+#ifdef VCB_UMMA_INSTRUMENT
+    if (getenv("VCB_UMMA_DEBUG")) sp.debug = atoi(getenv("VCB_UMMA_DEBUG"));
+#endif
+#ifdef VCB_UMMA_INSTRUMENT
+    static long long* trace_buf = nullptr;  // instrumented builds only (VCB_UMMA_TRACE): synchronises and prints
     if (getenv("VCB_UMMA_TRACE") != nullptr) {
       if (trace_buf == nullptr) cudaMalloc(&trace_buf, 64 * 8 * sizeof(long long));
       cudaMemset(trace_buf, 0, 64 * 8 * sizeof(long long));
       sp.trace = trace_buf;
     }
+#endif
     unsigned ev_flags = cudaEventRecordDefault;
     if (p->ev_stream_begin || p->ev_stream_end) {
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -759,6 +764,7 @@ static int run_umma(const vcb_problem_t* p, void* workspace, size_t ws_bytes, vo
     e = vcb_launch_umma_stream(sp, pl.n_tiles, pl.n_split, st);
     if (e != cudaSuccess) return (int)e;
     if (p->ev_stream_end) cudaEventRecordWithFlags((cudaEvent_t)p->ev_stream_end, st, ev_flags);
+#ifdef VCB_UMMA_INSTRUMENT
     if (sp.trace != nullptr) {
       static int printed = 0;
       long long h[64 * 8];
@@ -771,6 +777,7 @@ static int run_umma(const vcb_problem_t* p, void* workspace, size_t ws_bytes, vo
           printf("\n");
         }
     }
+#endif
   }
   {
     CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
