@@ -371,7 +371,8 @@ def run_ours(a):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item()) / n_e2e
             fmt_name = {1: "u8 + overflow list", 2: "u16", 4: "i32", 16: "2-bit codes + escape bytes + overflow list",
-                        32: "4-bit codes + escape bytes + overflow list"}
+                        32: "4-bit codes + escape bytes + overflow list",
+                        64: "2-bit codes + escape nibbles + escape bytes + overflow list"}
             e2e = {"value": Nc * world * Ng / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": n_e2e,
                    "note": ("both count matrices copied from pinned host memory every step in the staging format of "

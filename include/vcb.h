@@ -171,6 +171,13 @@ int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst,
 int vcb_expand_counts_packed(const uint32_t* codes, int32_t bits, const uint8_t* side, const int64_t* block_off, int64_t n,
                              float* dst, const int64_t* over_idx, const float* over_val, int64_t n_over, void* stream);
 
+/* Two-level variant of the 2-bit format: code 3 -> the next NIBBLE of `nibbles` (8 per little-endian 32-bit word, entry
+ * order) holding value-3 in 0..14; nibble 15 -> the next byte of `side` (value, 255 = overflow list).  block_off1[j] / block_off2[j]
+ * = nibbles / side bytes consumed before word 256*j.  0.30-0.45 bytes per entry for scRNA-seq counts. */
+int vcb_expand_counts_twolevel(const uint32_t* codes, const uint32_t* nibbles, const uint8_t* side, const int64_t* block_off1,
+                              const int64_t* block_off2, int64_t n, float* dst, const int64_t* over_idx, const float* over_val,
+                              int64_t n_over, void* stream);
+
 /* Value types of vcb_csr_to_counts (data_dtype). */
 #define VCB_CSR_F32 0
 #define VCB_CSR_I32 1

@@ -111,37 +111,57 @@ def test_expand_counts_argument_errors():
 
 # ---- sub-byte staging (2 / 4 bits per entry + escape side stream; vcb_expand_counts_packed) -------------------------------
 def _decode_sub_byte(h):
-    """Pure-torch restatement of the format (include/vcb.h) -- the oracle of the device decoder."""
-    bits = h.bits
-    per, E = 32 // bits, (1 << bits) - 1
+    """Pure-torch restatement of the formats (include/vcb.h) -- the oracle of the device decoders."""
     n = h.shape[0] * h.shape[1]
     w = h.staged.to(torch.int64) & 0xFFFFFFFF
-    codes = ((w[:, None] >> (torch.arange(per) * bits)) & E).reshape(-1)
-    cnt = (codes == E).reshape(-1, per * _lib.VCB_PACKED_BLOCK_WORDS).sum(1)
-    assert torch.equal(h.block_off, torch.cumsum(cnt, 0) - cnt)       # escapes before each block
-    out = codes[:n].clone().float()
-    esc = (out == E).nonzero().reshape(-1)
-    out[esc] = h.side[: esc.numel()].float()                             # escape bytes in entry order
+    if h.fmt == _lib.VCB_COUNTS_B2N:   # 2-bit codes -> nibble stream -> byte stream
+        per_block = 16 * _lib.VCB_PACKED_BLOCK_WORDS
+        codes = ((w[:, None] >> (torch.arange(16) * 2)) & 3).reshape(-1)
+        cnt1 = (codes == 3).reshape(-1, per_block).sum(1)
+        assert torch.equal(h.block_off, torch.cumsum(cnt1, 0) - cnt1)
+        e1 = (codes == 3).nonzero().reshape(-1)
+        nw = h.nibbles.to(torch.int64) & 0xFFFFFFFF
+        nib = ((nw[:, None] >> (torch.arange(8) * 4)) & 15).reshape(-1)[: e1.numel()]
+        cnt2 = torch.zeros(cnt1.numel(), dtype=torch.int64).index_add_(0, e1 // per_block, (nib == 15).long())
+        assert torch.equal(h.block_off2, torch.cumsum(cnt2, 0) - cnt2)
+        vals = (nib + 3).float()
+        e2 = (nib == 15).nonzero().reshape(-1)
+        vals[e2] = h.side[: e2.numel()].float()
+        out = codes.clone().float()
+        out[e1] = vals
+        out = out[:n]
+    else:
+        bits = h.bits
+        per, E = 32 // bits, (1 << bits) - 1
+        codes = ((w[:, None] >> (torch.arange(per) * bits)) & E).reshape(-1)
+        cnt = (codes == E).reshape(-1, per * _lib.VCB_PACKED_BLOCK_WORDS).sum(1)
+        assert torch.equal(h.block_off, torch.cumsum(cnt, 0) - cnt)       # escapes before each block
+        out = codes[:n].clone().float()
+        esc = (out == E).nonzero().reshape(-1)
+        out[esc] = h.side[: esc.numel()].float()                             # escape bytes in entry order
     if h.over_idx is not None:
-        out[h.over_idx] = h.over_val                                     # side byte 255 -> overflow list
+        out[h.over_idx] = h.over_val                                         # byte 255 -> overflow list
     return out.reshape(h.shape)
 
 
 def _sparse_matrix(lam, Nc, ld, seed=0):
+    """Poisson counts with a few planted values on every escape boundary (3, 17, 18, 19, 254, 255, 70000)."""
     g = torch.Generator().manual_seed(seed)
     M = torch.poisson(torch.full((Nc, ld), lam), generator=g)
     if Nc > 6 and ld > 6:
         M[3, 5], M[0, 0], M[5, 1], M[Nc - 1, ld - 1] = 255.0, 70000.0, 254.0, 16.0
+        M[2, 2], M[4, 4], M[6, 6], M[6, 5] = 17.0, 18.0, 19.0, 3.0
     return M
 
 
-@pytest.mark.parametrize("lam,shape,fmt", [(0.4, (3000, 2000), _lib.VCB_COUNTS_B2), (2.0, (777, 52), _lib.VCB_COUNTS_B4),
-                                           (3.7, (4100, 200), _lib.VCB_COUNTS_B4), (400.0, (300, 40), _lib.VCB_COUNTS_I32)])
+@pytest.mark.parametrize("lam,shape,fmt", [(0.4, (3000, 2000), _lib.VCB_COUNTS_B2N), (2.0, (777, 52), _lib.VCB_COUNTS_B2N),
+                                           (3.7, (4100, 200), _lib.VCB_COUNTS_B4), (0.4, (1, 4), _lib.VCB_COUNTS_B2),
+                                           (400.0, (300, 40), _lib.VCB_COUNTS_I32)])
 def test_sub_byte_format_choice_and_host_packing(lam, shape, fmt):
     M = _sparse_matrix(lam, *shape)
     h = HostCounts.from_tensor(M, sub_byte=True)
     assert h.fmt == fmt
-    if fmt in (_lib.VCB_COUNTS_B2, _lib.VCB_COUNTS_B4):
+    if fmt in (_lib.VCB_COUNTS_B2, _lib.VCB_COUNTS_B2N, _lib.VCB_COUNTS_B4):
         assert torch.equal(_decode_sub_byte(h), M)
         assert h.nbytes < 0.62 * M.numel() + 8192        # well under one byte per entry
     assert HostCounts.from_tensor(M).fmt in (_lib.VCB_COUNTS_U8, _lib.VCB_COUNTS_U16, _lib.VCB_COUNTS_I32)   # opt-in only
@@ -170,3 +190,5 @@ def test_expand_counts_packed_argument_errors():
     assert lib.vcb_expand_counts_packed(t.data_ptr(), 3, t.data_ptr(), o.data_ptr(), 16, t.data_ptr(), None, None, 0, None) == -2
     assert lib.vcb_expand_counts_packed(t.data_ptr(), 4, t.data_ptr(), o.data_ptr(), 16, t.data_ptr() + 4, None, None, 0, None) == -3
     assert lib.vcb_expand_counts_packed(t.data_ptr(), 2, t.data_ptr(), o.data_ptr(), 16, t.data_ptr(), None, None, 3, None) == -1
+    assert lib.vcb_expand_counts_twolevel(t.data_ptr(), None, t.data_ptr(), o.data_ptr(), o.data_ptr(), 16, t.data_ptr(), None, None, 0, None) == -1
+    assert lib.vcb_expand_counts_twolevel(t.data_ptr(), t.data_ptr(), t.data_ptr(), o.data_ptr(), o.data_ptr(), 16, t.data_ptr() + 4, None, None, 0, None) == -3

@@ -19,6 +19,7 @@ VCB_MAX_HARMONICS = 5
 VCB_COUNTS_U8, VCB_COUNTS_U16, VCB_COUNTS_I32 = 1, 2, 4
 VCB_CSR_F32, VCB_CSR_I32, VCB_CSR_F64, VCB_CSR_I64 = 0, 1, 2, 3
 VCB_COUNTS_B2, VCB_COUNTS_B4 = 16, 32  # HostCounts-only format tags: 2 / 4 bits per entry (vcb_expand_counts_packed)
+VCB_COUNTS_B2N = 64  # 2-bit codes -> nibble stream -> byte stream (vcb_expand_counts_twolevel)
 VCB_PACKED_BLOCK_WORDS = 256
 
 c_float_p = C.c_void_p  # device pointers travel as integers
@@ -56,6 +57,7 @@ EXPORTS = (
     "vcb_expand_counts",
     "vcb_csr_to_counts",
     "vcb_expand_counts_packed",
+    "vcb_expand_counts_twolevel",
     "vcb_clipped_adam",
 )
 
@@ -94,6 +96,9 @@ def load() -> C.CDLL:
     lib.vcb_expand_counts_packed.restype = C.c_int
     lib.vcb_expand_counts_packed.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_int64, C.c_void_p]
+    lib.vcb_expand_counts_twolevel.restype = C.c_int
+    lib.vcb_expand_counts_twolevel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.vcb_csr_to_counts.restype = C.c_int
     lib.vcb_csr_to_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p]

@@ -473,6 +473,71 @@ __global__ void __launch_bounds__(VCB_PACKED_BLOCK_WORDS) vcb_expand_packed_kern
   }
 }
 
+// block-wide exclusive scan of one int per thread (256 threads); s_warp: 8 ints of shared scratch
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int before = 0;
+  for (int i = 0; i < warp; ++i) before += s_warp[i];
+  __syncthreads();
+  return before + incl - v;
+}
+
+// Two-level 2-bit staging -> float32 (format: include/vcb.h, vcb_expand_counts_twolevel).
+__global__ void __launch_bounds__(VCB_PACKED_BLOCK_WORDS) vcb_expand_packed2_kernel(
+    const uint32_t* __restrict__ codes, const uint32_t* __restrict__ nibbles, const uint8_t* __restrict__ side,
+    const long long* __restrict__ block_off1, const long long* __restrict__ block_off2, long long n, long long n_blocks,
+    float* __restrict__ dst) {
+  __shared__ int s_warp[VCB_PACKED_BLOCK_WORDS / 32];
+  for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const long long w = blk * VCB_PACKED_BLOCK_WORDS + threadIdx.x;
+    const uint32_t word = __ldcs(codes + w);
+    int cnt1 = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) cnt1 += (((word >> (2 * k)) & 3u) == 3u) ? 1 : 0;
+    long long p1 = block_off1[blk] + block_exclusive_scan_256(cnt1, s_warp);
+    // this thread's nibbles, in entry order, and how many of them escape again
+    unsigned long long nib = 0ull;
+    int cnt2 = 0;
+    for (int j = 0; j < cnt1; ++j) {
+      const long long i = p1 + j;
+      const unsigned v = (nibbles[i >> 3] >> (4 * (int)(i & 7))) & 15u;
+      nib |= (unsigned long long)v << (4 * j);
+      cnt2 += (v == 15u) ? 1 : 0;
+    }
+    long long p2 = block_off2[blk] + block_exclusive_scan_256(cnt2, s_warp);
+    float v[16];
+    int j = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t c = (word >> (2 * k)) & 3u;
+      float x = (float)c;
+      if (c == 3u) {
+        const unsigned nv = (unsigned)(nib >> (4 * j)) & 15u;
+        ++j;
+        x = (nv == 15u) ? (float)side[p2++] : (float)(3u + nv);
+      }
+      v[k] = x;
+    }
+    const long long e0 = w * 16;
+    if (e0 + 16 <= n) {
+      float4* d4 = reinterpret_cast<float4*>(dst + e0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) __stcs(d4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    } else {
+      for (int k = 0; k < 16; ++k)
+        if (e0 + k < n) dst[e0 + k] = v[k];
+    }
+  }
+}
+
 __global__ void vcb_scatter_overflow_kernel(const long long* __restrict__ idx, const float* __restrict__ val,
                                             long long n, float* __restrict__ dst) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -1018,6 +1083,32 @@ int vcb_expand_counts_packed(const uint32_t* codes, int32_t bits, const uint8_t*
     vcb::vcb_expand_packed_kernel<2><<<(unsigned)grid, VCB_PACKED_BLOCK_WORDS, 0, st>>>(codes, side, (const long long*)block_off, n, n_blocks, dst);
   else
     vcb::vcb_expand_packed_kernel<4><<<(unsigned)grid, VCB_PACKED_BLOCK_WORDS, 0, st>>>(codes, side, (const long long*)block_off, n, n_blocks, dst);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (n_over > 0) {
+    const int bs = 256;
+    long long b = (n_over + bs - 1) / bs;
+    if (b > 148 * 8) b = 148 * 8;
+    vcb::vcb_scatter_overflow_kernel<<<(unsigned)b, bs, 0, st>>>((const long long*)over_idx, over_val, n_over, dst);
+    e = cudaGetLastError();
+  }
+  return (int)e;
+}
+
+int vcb_expand_counts_twolevel(const uint32_t* codes, const uint32_t* nibbles, const uint8_t* side, const int64_t* block_off1,
+                              const int64_t* block_off2, int64_t n, float* dst, const int64_t* over_idx, const float* over_val,
+                              int64_t n_over, void* stream) {
+  if (!codes || !nibbles || !side || !block_off1 || !block_off2 || !dst) return VCB_ERR_NULL;
+  if (n < 0 || n_over < 0) return VCB_ERR_SIZE;
+  if (n_over > 0 && (!over_idx || !over_val)) return VCB_ERR_NULL;
+  if ((((uintptr_t)codes) & 3) != 0 || (((uintptr_t)nibbles) & 3) != 0 || (((uintptr_t)dst) & 15) != 0) return VCB_ERR_ALIGN;
+  if (n == 0) return VCB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long per_block = (long long)VCB_PACKED_BLOCK_WORDS * 16;
+  const long long n_blocks = (n + per_block - 1) / per_block;
+  const long long grid = n_blocks < 148LL * 16 ? n_blocks : 148LL * 16;
+  vcb::vcb_expand_packed2_kernel<<<(unsigned)grid, VCB_PACKED_BLOCK_WORDS, 0, st>>>(
+      codes, nibbles, side, (const long long*)block_off1, (const long long*)block_off2, n, n_blocks, dst);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (n_over > 0) {

@@ -106,6 +106,7 @@ class HostCounts:
         self.staged, self.fmt, self.shape = staged, fmt, tuple(shape)
         self.over_idx, self.over_val = over_idx, over_val
         self.side, self.block_off = side, block_off  # sub-byte formats: escape bytes in entry order, escapes before each block
+        self.nibbles = self.block_off2 = None        # two-level 2-bit format: escape nibbles, second-level escapes before each block
         self._dev = None  # device staging buffers, created on first upload
 
     @property
@@ -116,12 +117,14 @@ class HostCounts:
             n += self.over_idx.numel() * 8 + self.over_val.numel() * 4
         if self.side is not None:
             n += self.side.numel() + self.block_off.numel() * 8
+        if self.nibbles is not None:
+            n += self.nibbles.numel() * 4 + self.block_off2.numel() * 8
         return n
 
     @property
     def bits(self) -> int:
         """Bits per entry of the main stream."""
-        return {_lib.VCB_COUNTS_B2: 2, _lib.VCB_COUNTS_B4: 4, _lib.VCB_COUNTS_U8: 8, _lib.VCB_COUNTS_U16: 16,
+        return {_lib.VCB_COUNTS_B2: 2, _lib.VCB_COUNTS_B2N: 2, _lib.VCB_COUNTS_B4: 4, _lib.VCB_COUNTS_U8: 8, _lib.VCB_COUNTS_U16: 16,
                 _lib.VCB_COUNTS_I32: 32}[self.fmt]
 
     @staticmethod
@@ -140,21 +143,25 @@ class HostCounts:
         assert M.dim() == 2
         Nc, ld = M.shape
         mx = float(M.max()) if M.numel() else 0.0
-        n_esc = n3 = n15 = 0
+        n_esc = n3 = n15 = n18 = 0
         for r0 in range(0, Nc, chunk_rows):
             blk = M[r0: r0 + chunk_rows]
             n_esc += int((blk >= cls.ESCAPE).sum())
             if sub_byte:
                 n3 += int((blk >= 3).sum())
                 n15 += int((blk >= 15).sum())
+                n18 += int((blk >= 18).sum())
         fmt = cls.choose_format(mx, n_esc / max(1, M.numel()))
         if sub_byte and M.numel() and ld % 4 == 0 and mx < 2 ** 24:
             n = M.numel()
             over = 12 * n_esc  # counts >= 255 travel as (int64 index, float32 value) pairs in every byte / sub-byte format
             size = {_lib.VCB_COUNTS_B2: n / 4 + n3 + over, _lib.VCB_COUNTS_B4: n / 2 + n15 + over,
+                    _lib.VCB_COUNTS_B2N: n / 4 + n3 / 2 + n18 + over,
                     fmt: n * {_lib.VCB_COUNTS_U8: 1, _lib.VCB_COUNTS_U16: 2, _lib.VCB_COUNTS_I32: 4}[fmt]
                     + (over if fmt == _lib.VCB_COUNTS_U8 else 0)}
             best = min(size, key=size.get)
+            if best == _lib.VCB_COUNTS_B2N:
+                return cls._pack_two_level(M, n_esc, n3)
             if best in (_lib.VCB_COUNTS_B2, _lib.VCB_COUNTS_B4):
                 return cls._pack_sub_byte(M, 2 if best == _lib.VCB_COUNTS_B2 else 4, best, n_esc)
         tdt = {_lib.VCB_COUNTS_U8: torch.uint8, _lib.VCB_COUNTS_U16: torch.uint16, _lib.VCB_COUNTS_I32: torch.int32}[fmt]
@@ -229,13 +236,83 @@ class HostCounts:
                 over_idx, over_val = over_idx.pin_memory(), over_val.pin_memory()
         return cls(codes, fmt, (Nc, ld), over_idx, over_val, side=side, block_off=block_off)
 
+    @classmethod
+    def _pack_two_level(cls, M: torch.Tensor, n_over: int, n3: int) -> "HostCounts":
+        """2-bit codes (3 = escape) -> nibble stream (value-3; 15 = escape) -> byte stream (value; 255 -> overflow list).
+        Format: include/vcb.h, vcb_expand_counts_twolevel."""
+        Nc, ld = M.shape
+        n = Nc * ld
+        per, per_block = 16, 16 * _lib.VCB_PACKED_BLOCK_WORDS
+        n_blocks = (n + per_block - 1) // per_block
+        pin = torch.cuda.is_available()
+        codes = torch.zeros(n_blocks * _lib.VCB_PACKED_BLOCK_WORDS, dtype=torch.int32, pin_memory=pin)
+        nib_words = torch.zeros(max(1, (n3 + 7) // 8), dtype=torch.int32, pin_memory=pin)
+        esc1 = torch.zeros(n_blocks, dtype=torch.int64)
+        esc2 = torch.zeros(n_blocks, dtype=torch.int64)
+        rows = (1 << 16) // 1024 * 1024
+        dev = M.device
+        sh2 = (torch.arange(16, dtype=torch.int64, device=dev) * 2)
+        sh4 = (torch.arange(8, dtype=torch.int64, device=dev) * 4)
+        to_i32 = lambda w: torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32)
+        carry = torch.zeros(0, dtype=torch.int64, device=dev)  # nibbles that did not fill a word yet
+        nib_done = 0
+        side, idx, val = [], [], []
+        for r0 in range(0, Nc, rows):
+            flat = M[r0: r0 + rows].reshape(-1)
+            e0 = r0 * ld
+            pad = (-flat.numel()) % per_block
+            if pad:
+                flat = torch.cat([flat, flat.new_zeros(pad)])
+            m1 = flat >= 3
+            v1 = flat[m1]
+            m2 = v1 >= 18
+            side.append(v1[m2].clamp(max=cls.ESCAPE).to(torch.uint8).cpu())
+            if n_over:
+                nz = (flat >= cls.ESCAPE).nonzero().reshape(-1)
+                idx.append((nz + e0).to(torch.int64).cpu())
+                val.append(flat[nz].to(torch.float32).cpu())
+            words = to_i32((flat.clamp(max=3).to(torch.int64).reshape(-1, per) << sh2).sum(1))
+            w0 = e0 // per
+            codes[w0: w0 + words.numel()].copy_(words)
+            b0 = e0 // per_block
+            c1 = m1.reshape(-1, per_block).sum(1).to(torch.int64)
+            esc1[b0: b0 + c1.numel()] = c1.cpu()
+            # second-level escapes per block: scatter-add the flags of the escaped entries into their blocks
+            blk_of = (m1.nonzero().reshape(-1) // per_block)
+            c2 = torch.zeros(c1.numel(), dtype=torch.int64, device=dev).index_add_(0, blk_of, m2.to(torch.int64))
+            esc2[b0: b0 + c2.numel()] = c2.cpu()
+            nibs = torch.cat([carry, (v1 - 3).clamp(max=15).to(torch.int64)])
+            whole = nibs.numel() // 8 * 8
+            if whole:
+                nw = to_i32((nibs[:whole].reshape(-1, 8) << sh4).sum(1))
+                nib_words[nib_done: nib_done + nw.numel()].copy_(nw)
+                nib_done += nw.numel()
+            carry = nibs[whole:]
+        if carry.numel():
+            last = torch.cat([carry, carry.new_zeros(8 - carry.numel())])
+            nib_words[nib_done: nib_done + 1].copy_(to_i32((last.reshape(1, 8) << sh4).sum(1)))
+        side = torch.cat(side) if side else torch.zeros(0, dtype=torch.uint8)
+        if side.numel() == 0:
+            side = torch.zeros(1, dtype=torch.uint8)
+        off1 = torch.cumsum(esc1, 0) - esc1
+        off2 = torch.cumsum(esc2, 0) - esc2
+        over_idx = torch.cat(idx) if n_over else None
+        over_val = torch.cat(val) if n_over else None
+        if pin:
+            side, off1, off2 = side.pin_memory(), off1.pin_memory(), off2.pin_memory()
+            if n_over:
+                over_idx, over_val = over_idx.pin_memory(), over_val.pin_memory()
+        h = cls(codes, _lib.VCB_COUNTS_B2N, (Nc, ld), over_idx, over_val, side=side, block_off=off1)
+        h.nibbles, h.block_off2 = nib_words, off2
+        return h
+
     # ---- device side: two sets of staging buffers, so that the H2D copy of the next upload overlaps the work on the last one
     def _device_set(self, dev, k: int):
         if self._dev is None or self._dev[0][0].device != dev:
             def mk(t):
                 return None if t is None else torch.empty_like(t, device=dev)
-            self._dev = [[mk(self.staged), mk(self.over_idx), mk(self.over_val), mk(self.side), mk(self.block_off), None]
-                         for _ in range(2)]
+            self._dev = [[mk(self.staged), mk(self.over_idx), mk(self.over_val), mk(self.side), mk(self.block_off), None,
+                          mk(self.nibbles), mk(self.block_off2)] for _ in range(2)]
             self._next, self._pending = 0, None
         return self._dev[k]
 
@@ -254,7 +331,8 @@ class HostCounts:
         if bufs[5] is not None:
             stream.wait_event(bufs[5])  # the widening kernel that last read this set has finished
         with torch.cuda.stream(stream):
-            for d, h in zip(bufs[:5], (self.staged, self.over_idx, self.over_val, self.side, self.block_off)):
+            for d, h in zip(bufs[:5] + bufs[6:8], (self.staged, self.over_idx, self.over_val, self.side, self.block_off,
+                                                   self.nibbles, self.block_off2)):
                 if d is not None:
                     d.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
@@ -274,10 +352,14 @@ class HostCounts:
         self._pending = None
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(ev)
-        d_st, d_i, d_v, d_side, d_off, _ = self._dev[k]
+        d_st, d_i, d_v, d_side, d_off, _, d_nib, d_off2 = self._dev[k]
         n_over = 0 if d_i is None else d_i.numel()
         lib = _lib.load()
-        if d_side is not None:
+        if d_nib is not None:
+            _lib.check(lib.vcb_expand_counts_twolevel(d_st.data_ptr(), d_nib.data_ptr(), d_side.data_ptr(), d_off.data_ptr(),
+                                                      d_off2.data_ptr(), dst.numel(), dst.data_ptr(), _ptr(d_i), _ptr(d_v), n_over,
+                                                      cur.cuda_stream), "vcb_expand_counts_twolevel")
+        elif d_side is not None:
             _lib.check(lib.vcb_expand_counts_packed(d_st.data_ptr(), self.bits, d_side.data_ptr(), d_off.data_ptr(), dst.numel(),
                                                     dst.data_ptr(), _ptr(d_i), _ptr(d_v), n_over, cur.cuda_stream),
                        "vcb_expand_counts_packed")
