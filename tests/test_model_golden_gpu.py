@@ -105,6 +105,33 @@ def test_conditioned_velocity_fit_driver_runs_and_matches():
     assert fit.posterior["νω"].shape[0] == 4 and fit.posterior["ω"].shape[-1] == mp.Nc
     # conditioned sites receive no updates
     assert torch.equal(pyro.param("ϕxy_locs").detach().cpu(), inp["phixy_prior"].float())
+    # the estimates come back as container objects, like the reference's fit() (velocity_inference_model.py:160-277)
+    K, Kw = mp.μνg.shape[-1], mp.Nhω
+    assert fit.cycle_pyro.means.shape == (K, mp.Ng) and fit.cycle_pyro.stds.shape == (K, mp.Ng)
+    assert np.array_equal(fit.cycle_pyro.means.values, fit.fourier_coef)
+    assert fit.cycle_pyro.log_betas.shape == (mp.Ng,) and fit.cycle_pyro.log_gammas.shape == (mp.Ng,)
+    assert fit.cycle_pyro.disp_pyro.shape == (mp.Ng,)
+    assert tuple(fit.phase_pyro.phis.shape) == (mp.Nc,) and float(fit.phase_pyro.phis.min()) >= 0.0
+    assert fit.speed_pyro.means.shape == (Kw, mp.Nx) and list(fit.speed_pyro.means.index)[0] == "nu0"
+
+
+def test_phase_fit_driver_returns_containers():
+    from velocycle_b200 import ppl as pyro
+    from velocycle_b200.phase_inference_model import PhaseFitModel
+    from velocycle_b200.ppl.optim import ClippedAdam
+
+    z, inp = load("case_stereo")
+    mp = _mp(inp, "phase")
+    pyro.clear_param_store()
+    pyro.set_rng_seed(5)
+    fit = PhaseFitModel(mp, num_samples=2, n_per_bin=2)
+    fit.fit(ClippedAdam({"lr": 0.03, "betas": (0.8, 0.99)}), num_steps=8, verbose=False)
+    assert len(fit.losses) == 8 and np.isfinite(fit.losses).all()
+    K = mp.μνg.shape[-1]
+    assert fit.cycle_pyro.means.shape == (K, mp.Ng) and np.array_equal(fit.cycle_pyro.stds.values, fit.fourier_coef_sd)
+    assert fit.cycle_pyro.disp_pyro.shape == (mp.Ng,)
+    assert fit.phase_pyro.phi_xy.shape == (2, mp.Nc)
+    assert np.array_equal(fit.phase_pyro.phi_xy_tensor.numpy(), fit.phis_pyro.astype(np.float32))
 
 
 @pytest.mark.parametrize("kind", ["phase", "velocity", "velocity_lrmn"])

@@ -117,6 +117,16 @@ class PhaseFitModel:
         self.disp_pyro = pyro.param("shape_inv_locs").detach().squeeze().cpu().numpy().T
         if self.metaparams.with_delta_nu:
             self.delta_nus = pyro.param("Δν_locs").detach().unsqueeze(-3).unsqueeze(-4).float().cpu().numpy()
+        # the estimates as new container objects (phase_inference_model.py:186-194); gene / cell names come from the priors
+        from .cycle import Cycle
+        from .phases import Phases
+
+        mp = self.metaparams
+        genes = getattr(getattr(mp, "cycle_prior", None), "genes", None)
+        cells = getattr(getattr(getattr(mp, "phase_prior", None), "phi_xy", None), "columns", None)
+        self.cycle_pyro = Cycle.from_array(np.atleast_2d(self.fourier_coef), np.atleast_2d(self.fourier_coef_sd), genes)
+        self.cycle_pyro.set_disp_pyro(self.disp_pyro)
+        self.phase_pyro = Phases.from_array(self.phis_pyro, cell_names=cells)
         if self.get_posterior and self.num_samples > 0:
             nbins = int(np.ceil(self.num_samples / self.n_per_bin))
             rs = ["ν", "ϕxy", "ϕ", "ζ", "shape_inv"] + (["Δν"] if self.metaparams.with_delta_nu else [])

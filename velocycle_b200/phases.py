@@ -1,0 +1,119 @@
+"""``Phases``: per-cell phase estimates as (phi_x, phi_y) direction vectors -- the container the preprocessing reads
+(``phi_xy_tensor``: ``preprocessing.py:130``) and the fit drivers fill (``phase_inference_model.py:199``).  Same attributes,
+methods and CSV format as ``velocycle/phases.py`` for everything on or next to the SVI path; the PCA heuristic and the
+grid-search MLE (``phases.py:307-383, 450-509``) are not restated here.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .utils import pack_direction, unpack_direction
+
+__all__ = ["Phases"]
+
+_ROWS = ["phi_x", "phi_y"]
+
+
+class Phases:
+    def __init__(self):
+        self.phi_xy = None   # pd.DataFrame (2, Nc): rows phi_x, phi_y; columns = cell names
+        self.pcs = None
+        self.omegas = None
+
+    def __len__(self) -> int:
+        return self.shape[-1]
+
+    @property
+    def shape(self):
+        return self.phi_xy.shape
+
+    def set_phixy(self, new_phixy) -> None:
+        if isinstance(new_phixy, pd.DataFrame):
+            self.phi_xy = new_phixy
+            return
+        if isinstance(new_phixy, torch.Tensor):
+            new_phixy = new_phixy.detach().cpu().numpy()
+        if not isinstance(new_phixy, np.ndarray):
+            raise Exception("Error: invalid type for new_phixy")
+        self.phi_xy = pd.DataFrame(new_phixy, index=self.phi_xy.index, columns=self.phi_xy.columns)
+
+    def set_omegas(self, new_omegas) -> None:
+        self.omegas = new_omegas
+
+    # ---- views ----------------------------------------------------------------------------------------------
+    @property
+    def phi_xy_tensor(self) -> torch.Tensor:
+        return torch.tensor(self.phi_xy.values.astype(np.float32))
+
+    @property
+    def phis(self) -> torch.Tensor:
+        """Angles in [0, 2 pi) (``phases.py:176-186``)."""
+        phis = pack_direction(self.phi_xy_tensor.T)
+        phis[phis < 0] = phis[phis < 0] + 2 * np.pi
+        return phis
+
+    @property
+    def directions(self) -> np.ndarray:
+        return np.arctan2(self.phi_xy.values[1, :], self.phi_xy.values[0, :]) % (2 * np.pi)
+
+    @property
+    def concentrations(self) -> np.ndarray:
+        return np.sqrt(np.sum(self.phi_xy.values ** 2, 0))
+
+    @property
+    def stds(self) -> np.ndarray:
+        """Circular standard deviation of a von Mises with these concentrations: sqrt(1 - I1(k)/I0(k)) (``phases.py:218-234``;
+        the Bessel ratio comes from the exponentially scaled torch.special functions instead of polynomial fits)."""
+        k = torch.as_tensor(self.concentrations, dtype=torch.float64)
+        return np.sqrt(1.0 - (torch.special.i1e(k) / torch.special.i0e(k)).numpy())
+
+    # ---- files ----------------------------------------------------------------------------------------------
+    @classmethod
+    def load(cls, filepath) -> "Phases":
+        out = cls()
+        out.phi_xy = pd.read_csv(filepath, index_col=0)
+        return out
+
+    @classmethod
+    def from_file(cls, filepath) -> "Phases":
+        return cls.load(filepath)
+
+    def save(self, pathname) -> None:
+        self.phi_xy.to_csv(pathname)
+
+    # ---- constructors ---------------------------------------------------------------------------------------
+    @classmethod
+    def from_array(cls, phi_xy_array, cell_names=None) -> "Phases":
+        assert phi_xy_array.shape[0] == 2, "Shape of the array is incorrect"
+        if cell_names is not None:
+            assert len(cell_names) == phi_xy_array.shape[1]
+        out = cls()
+        out.phi_xy = pd.DataFrame(phi_xy_array, index=_ROWS, columns=cell_names)
+        return out
+
+    @classmethod
+    def flat_prior(cls, anndata_object) -> "Phases":
+        """All-zero direction vectors = no phase information (``phases.py:384-402``)."""
+        out = cls()
+        out.phi_xy = pd.DataFrame(np.zeros((2, anndata_object.shape[0])), index=_ROWS, columns=anndata_object.obs.index)
+        return out
+
+    # ---- gauge ----------------------------------------------------------------------------------------------
+    def shift_zero(self, gene=None, phase=None) -> None:
+        """Subtract ``phase`` from every angle; the result has unit concentration (``phases.py:404-421``)."""
+        if gene is not None:
+            raise Exception("Error: must phase for desired shift")
+        if phase is None:
+            raise Exception("Error: must specify gene or phase for desired shift")
+        self.set_phixy(unpack_direction(self.phis - phase).T)
+
+    def rotate(self, angle=None) -> None:
+        if angle is None:
+            raise Exception("Error: must specify angle for desired rotation")
+        c, s = np.cos(angle), np.sin(angle)
+        self.set_phixy(np.matmul(np.array([[c, -s], [s, c]]), self.phi_xy.values))
+
+    def invert_direction(self) -> None:
+        self.set_phixy(np.matmul(np.array([[1.0, 0.0], [0.0, -1.0]]), self.phi_xy.values))

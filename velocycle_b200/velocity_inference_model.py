@@ -152,6 +152,22 @@ class VelocityFitModel:
             self.velocity_coef = pyro.param("νω_locs").detach().unsqueeze(-3).unsqueeze(-4).float().cpu().numpy()
             self.velocity_coef_sd = pyro.param("νω_scales").detach().unsqueeze(-3).unsqueeze(-4).float().cpu().numpy()
         self.log_betas = pyro.param("logβg_locs").detach().squeeze().cpu().numpy().T
+        # the estimates as new container objects (velocity_inference_model.py:160-186); names come from the priors
+        from .angularspeed import AngularSpeed
+        from .cycle import Cycle
+        from .phases import Phases
+
+        genes = getattr(getattr(mp, "cycle_prior", None), "genes", None)
+        cells = getattr(getattr(getattr(mp, "phase_prior", None), "phi_xy", None), "columns", None)
+        conds = getattr(getattr(mp, "speed_prior", None), "conditions", None)
+        self.cycle_pyro = Cycle.from_array(np.atleast_2d(self.fourier_coef), np.atleast_2d(self.fourier_coef_sd), genes)
+        self.cycle_pyro.set_log_betas(self.log_betas)
+        self.cycle_pyro.set_disp_pyro(self.disp_pyro)
+        self.phase_pyro = Phases.from_array(self.phis_pyro, cell_names=cells)
+        if mp.model_type != "lrmn":
+            self.cycle_pyro.set_log_gammas(self.log_gammas)
+            self.speed_pyro = AngularSpeed.from_array(condition_names=conds, means_array=self.velocity_coef.squeeze(),
+                                                      stds_array=self.velocity_coef_sd.squeeze(), Nhω=mp.Nhω)
         if self.get_posterior and self.num_samples > 0:
             nbins = int(np.ceil(self.num_samples / self.n_per_bin))
             bins = [self.sample_posterior(num_samples=self.n_per_bin, rs=self._return_sites()) for _ in range(nbins)]
@@ -160,6 +176,9 @@ class VelocityFitModel:
                 self.log_gammas = self.posterior["logγg"].mean(0).squeeze().numpy().T
                 self.velocity_coef = self.posterior["νω"].mean(0).float().numpy()
                 self.velocity_coef_sd = self.posterior["νω"].std(0).float().numpy()
+                self.cycle_pyro.set_log_gammas(self.log_gammas)
+                self.speed_pyro = AngularSpeed.from_array(condition_names=conds, means_array=self.velocity_coef.squeeze(),
+                                                          stds_array=self.velocity_coef_sd.squeeze(), Nhω=mp.Nhω)
         if store_output:
             return intermediate_output
 
