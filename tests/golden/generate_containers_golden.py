@@ -25,10 +25,15 @@ REF = "/root/reference/velocycle"
 
 
 def load_reference():
-    for name in ("matplotlib", "matplotlib.pyplot", "pyro", "pyro.distributions"):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from velocycle_b200 import ppl
+    from velocycle_b200.ppl import distributions
+
+    for name in ("matplotlib", "matplotlib.pyplot"):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    sys.modules["pyro"].distributions = sys.modules["pyro.distributions"]
+    sys.modules["pyro"] = ppl                      # Pyro is not installable offline: its restatement (Poisson, GammaPoisson)
+    sys.modules["pyro.distributions"] = distributions
     pkg = types.ModuleType("velocycle")
     pkg.__path__ = [REF]
     sys.modules["velocycle"] = pkg
@@ -105,6 +110,27 @@ def main():
     p3 = Phases.from_array(xy.copy(), cells)
     p3.shift_zero(phase=1.1)
     rec["phases_shifted"] = p3.phi_xy.values
+
+    # grid-search MLE prior and max_corr on a small seeded data set drawn around a known cycle
+    from types import SimpleNamespace
+    import torch
+    true_phi = rng.uniform(0, 2 * np.pi, size=40)
+    cyc_mle = Cycle.from_array(np.vstack([rng.normal(0.5, 0.3, size=(1, 6)), rng.normal(0, 0.8, size=(2, 6))]), np.ones((3, 6)), genes)
+    zeta = np.stack([np.ones(40), np.sin(true_phi), np.cos(true_phi)], 1)
+    n_sc = rng.integers(50, 150, size=40).astype(float)
+    lam = np.exp(zeta @ cyc_mle.means.values + 0.5 * np.log(n_sc)[:, None])
+    S_mle = rng.poisson(lam).astype(np.int64)
+    data = SimpleNamespace(obs=SimpleNamespace(n_scounts=SimpleNamespace(values=n_sc)), layers={"spliced": S_mle})
+    rec["mle_means"], rec["mle_n_scounts"], rec["mle_S"] = cyc_mle.means.values, n_sc, S_mle
+    for nm in ("Poisson", "NegativeBinomial"):
+        pm = Phases.from_array(np.zeros((2, 40)), [f"c{i}" for i in range(40)])
+        pm.from_cycle_mle(cyc_mle, data, a=0.5, bins=50, concentration=7.0, noisemodel=nm, dispersion=0.4)
+        rec[f"mle_phixy_{nm}"] = pm.phi_xy.values
+    pc = Phases.from_array(xy.copy(), cells)
+    mc_in = rng.normal(size=9)
+    sh, cbest, call = pc.max_corr(mc_in, npoints=20)
+    rec["maxcorr_in"], rec["maxcorr_all"] = mc_in, np.array(call)
+    rec["maxcorr_shift"], rec["maxcorr_best"] = np.array(sh), np.array(cbest)
 
     am, asd = rng.normal(size=(3, 2)), rng.uniform(0.05, 0.5, size=(3, 2))
     sp = AngularSpeed.from_array(am, asd, conds, Nhω=3)

@@ -140,3 +140,28 @@ def test_angular_speed(gold, tmp_path):
     assert np.array_equal(t.means.values, gold["speed_trivial_means"]) and np.array_equal(t.stds.values, gold["speed_trivial_stds"])
     t.extend(["third"])
     assert t.conditions == CONDS + ["third"] and float(t.stds["third"].iloc[0]) == 3.0
+
+
+def test_phases_from_cycle_mle_and_max_corr(gold):
+    """The grid-search maximum-likelihood prior (phases.py:471-509) and max_corr against the reference's own run."""
+    from types import SimpleNamespace
+
+    cyc = Cycle.from_array(gold["mle_means"], np.ones((3, 6)), GENES)
+    data = SimpleNamespace(obs=SimpleNamespace(n_scounts=SimpleNamespace(values=gold["mle_n_scounts"])),
+                           layers={"spliced": gold["mle_S"]})
+    for nm in ("Poisson", "NegativeBinomial"):
+        p = Phases.from_array(np.zeros((2, 40)), [f"c{i}" for i in range(40)])
+        p.from_cycle_mle(cyc, data, a=0.5, bins=50, concentration=7.0, noisemodel=nm, dispersion=0.4, bins_per_pass=7)
+        assert np.array_equal(p.phi_xy.values, gold[f"mle_phixy_{nm}"]), nm          # same arg-max bin for every cell
+        assert np.allclose(p.concentrations, 7.0, atol=1e-5)
+    import scipy.sparse as sp
+    data_sp = SimpleNamespace(obs=data.obs, layers={"spliced": sp.csr_matrix(gold["mle_S"])})   # sparse layer
+    q = Phases.from_array(np.zeros((2, 40)), [f"c{i}" for i in range(40)])
+    q.from_cycle_mle(cyc, data_sp, a=0.5, bins=50, concentration=7.0)
+    assert np.array_equal(q.phi_xy.values, gold["mle_phixy_Poisson"])
+    with pytest.raises(NotImplementedError):
+        q.from_cycle_mle(cyc, data, noisemodel="Lognormal")
+    m = Phases.from_array(gold["phases_in"].copy(), CELLS)
+    shift, best, allc = m.max_corr(gold["maxcorr_in"], npoints=20)
+    assert shift == float(gold["maxcorr_shift"]) and np.allclose(allc, gold["maxcorr_all"], rtol=0, atol=1e-12)
+    assert np.isclose(best, float(gold["maxcorr_best"]), rtol=0, atol=1e-12)

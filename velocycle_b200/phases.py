@@ -1,7 +1,7 @@
 """``Phases``: per-cell phase estimates as (phi_x, phi_y) direction vectors -- the container the preprocessing reads
 (``phi_xy_tensor``: ``preprocessing.py:130``) and the fit drivers fill (``phase_inference_model.py:199``).  Same attributes,
-methods and CSV format as ``velocycle/phases.py`` for everything on or next to the SVI path; the PCA heuristic and the
-grid-search MLE (``phases.py:307-383, 450-509``) are not restated here.
+methods and CSV format as ``velocycle/phases.py`` for everything on or next to the SVI path, including the grid-search maximum-likelihood prior (``from_cycle_mle``) and
+``max_corr``; the PCA heuristic (``phases.py:307-383``, needs scikit-learn on an AnnData) is not restated.
 """
 from __future__ import annotations
 
@@ -9,7 +9,7 @@ import numpy as np
 import pandas as pd
 import torch
 
-from .utils import pack_direction, unpack_direction
+from .utils import pack_direction, torch_fourier_basis, unpack_direction
 
 __all__ = ["Phases"]
 
@@ -117,3 +117,56 @@ class Phases:
 
     def invert_direction(self) -> None:
         self.set_phixy(np.matmul(np.array([[1.0, 0.0], [0.0, -1.0]]), self.phi_xy.values))
+
+    # ---- data-driven phases -----------------------------------------------------------------------------------
+    def max_corr(self, counts, npoints: int = 100):
+        """Shift in [0, 2 pi) that maximises the correlation of the (shifted, re-wrapped) phases with ``counts``
+        (``phases.py:450-469``).  Returns (shift, correlation, all correlations)."""
+        shifts = np.arange(0, npoints) / npoints * 2 * np.pi
+        base = self.phis                                  # float32, like the reference's arithmetic
+        corr = []
+        for sh in shifts:
+            x = base - sh
+            x[x < 0] = x[x < 0] + 2 * np.pi
+            corr.append(np.corrcoef(x.numpy(), counts)[0, 1])
+        best = int(np.argmax(np.array(corr)))
+        return shifts[best], corr[best], corr
+
+    def from_cycle_mle(self, cycle, data, a=1, bins: int = 100, concentration: float = 10.0, noisemodel: str = "Poisson",
+                       dispersion: float = 0.3, device=None, bins_per_pass: int = 8) -> None:
+        """Grid-search maximum-likelihood phase per cell given a Cycle (``phases.py:471-509``): for ``bins`` phases on a
+        regular grid, log P[bin, cell] = sum_g log p(S[c, g] | exp(nu_g . zeta(phi_bin) + a log n_scounts_c)) under a Poisson or
+        negative-binomial (``GammaPoisson(1/dispersion, 1/(dispersion mu))``) model; every cell takes the arg-max phase with the
+        given concentration.  The (bins, Ng, Nc) scan is evaluated ``bins_per_pass`` phases at a time on ``device`` (default: CPU;
+        pass a CUDA device for large data) -- the reference materialises it whole."""
+        if noisemodel not in ("Poisson", "NegativeBinomial"):
+            raise NotImplementedError("Not implemented yet, sorry")
+        dev = torch.device("cpu") if device is None else torch.device(device)
+        fou = cycle.means_tensor.to(dev)                                    # (K, Ng)
+        H = (fou.shape[0] - 1) // 2
+        log_counts = torch.tensor(np.log(data.obs.n_scounts.values), dtype=torch.float32, device=dev)
+        offset = log_counts * torch.as_tensor(a, device=dev)                # (Nc,)
+        layer = data.layers["spliced"]
+        layer = layer.toarray() if hasattr(layer, "toarray") else np.asarray(layer)
+        k = torch.as_tensor(layer.astype(np.int64), device=dev).T.to(torch.float32)   # (Ng, Nc)
+        grid = 2 * np.pi * torch.arange(0, 1, 1.0 / bins, dtype=torch.float32)
+        curves = torch.matmul(torch_fourier_basis(grid, num_harmonics=H).to(dev), fou)  # (bins, Ng)
+        lgk1 = torch.lgamma(k + 1.0)
+        r = 1.0 / dispersion
+        best_lp = torch.full((k.shape[1],), -float("inf"), device=dev)
+        best_bin = torch.zeros(k.shape[1], dtype=torch.long, device=dev)
+        for b0 in range(0, grid.shape[0], bins_per_pass):
+            eta = curves[b0: b0 + bins_per_pass, :, None] + offset[None, None, :]       # (b, Ng, Nc)
+            if noisemodel == "Poisson":
+                lp = k * eta - torch.exp(eta) - lgk1
+            else:  # NB with total_count r and mean mu = exp(eta): log-pmf of GammaPoisson(r, r / mu)
+                mu = torch.exp(eta)
+                lp = (torch.lgamma(k + r) - lgk1 - torch.lgamma(torch.as_tensor(r, device=dev))
+                      + r * (np.log(r) - torch.log(r + mu)) + k * (eta - torch.log(r + mu)))
+            tot = lp.sum(1)                                                             # (b, Nc)
+            val, idx = tot.max(0)
+            better = val > best_lp                                                      # strict: first maximum wins, like argmax
+            best_lp = torch.where(better, val, best_lp)
+            best_bin = torch.where(better, idx + b0, best_bin)
+        phis_mle = grid[best_bin.cpu()]
+        self.set_phixy((concentration * unpack_direction(phis_mle).T).numpy())
