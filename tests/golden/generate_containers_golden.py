@@ -132,6 +132,15 @@ def main():
     rec["maxcorr_in"], rec["maxcorr_all"] = mc_in, np.array(call)
     rec["maxcorr_shift"], rec["maxcorr_best"] = np.array(sh), np.array(cbest)
 
+    # PCA heuristic on a seeded ring-shaped data set
+    ang = rng.uniform(0, 2 * np.pi, size=60)
+    load = rng.normal(size=(2, 12))
+    Lz = np.exp(1.0 + 0.8 * (np.stack([np.cos(ang), np.sin(ang)], 1) @ load) + 0.1 * rng.normal(size=(60, 12)))
+    ad = SimpleNamespace(layers={"S_sz": Lz}, obs=SimpleNamespace(index=[f"k{i}" for i in range(60)]))
+    rec["pca_layer"] = Lz
+    for tag, kw in (("plain", {}), ("gap", dict(zero_at_min_density=True, concentration=3.0)), ("raw", dict(normalize_pcs=False))):
+        rec[f"pca_phixy_{tag}"] = Phases.from_pca_heuristic(ad, **kw).phi_xy.values
+
     am, asd = rng.normal(size=(3, 2)), rng.uniform(0.05, 0.5, size=(3, 2))
     sp = AngularSpeed.from_array(am, asd, conds, Nhω=3)
     sp.save(os.path.join(OUT, "angularspeed.csv"))

@@ -165,3 +165,15 @@ def test_phases_from_cycle_mle_and_max_corr(gold):
     shift, best, allc = m.max_corr(gold["maxcorr_in"], npoints=20)
     assert shift == float(gold["maxcorr_shift"]) and np.allclose(allc, gold["maxcorr_all"], rtol=0, atol=1e-12)
     assert np.isclose(best, float(gold["maxcorr_best"]), rtol=0, atol=1e-12)
+
+
+def test_phases_from_pca_heuristic(gold):
+    from types import SimpleNamespace
+
+    ad = SimpleNamespace(layers={"S_sz": gold["pca_layer"]}, obs=SimpleNamespace(index=[f"k{i}" for i in range(60)]))
+    for tag, kw in (("plain", {}), ("gap", dict(zero_at_min_density=True, concentration=3.0)), ("raw", dict(normalize_pcs=False))):
+        p = Phases.from_pca_heuristic(ad, **kw)
+        assert np.allclose(p.phi_xy.values, gold[f"pca_phixy_{tag}"], rtol=0, atol=1e-12), tag
+        assert p.pcs.shape == (60, 2) and list(p.phi_xy.columns)[:2] == ["k0", "k1"]
+    with pytest.raises(ValueError):
+        Phases.from_pca_heuristic(ad, layer="nope")

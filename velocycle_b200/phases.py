@@ -1,7 +1,7 @@
 """``Phases``: per-cell phase estimates as (phi_x, phi_y) direction vectors -- the container the preprocessing reads
 (``phi_xy_tensor``: ``preprocessing.py:130``) and the fit drivers fill (``phase_inference_model.py:199``).  Same attributes,
 methods and CSV format as ``velocycle/phases.py`` for everything on or next to the SVI path, including the grid-search maximum-likelihood prior (``from_cycle_mle``) and
-``max_corr``; the PCA heuristic (``phases.py:307-383``, needs scikit-learn on an AnnData) is not restated.
+``max_corr`` and the PCA heuristic (plotting excluded).
 """
 from __future__ import annotations
 
@@ -98,6 +98,36 @@ class Phases:
         """All-zero direction vectors = no phase information (``phases.py:384-402``)."""
         out = cls()
         out.phi_xy = pd.DataFrame(np.zeros((2, anndata_object.shape[0])), index=_ROWS, columns=anndata_object.obs.index)
+        return out
+
+    @classmethod
+    def from_pca_heuristic(cls, anndata_object, genes_to_use=None, concentration=1.0, layer="S_sz", small_count=1.0e-1,
+                           normalize_pcs=True, zero_at_min_density=False, random_state=0, plot=False, n_components=2) -> "Phases":
+        """Phase = angle in the plane of the first two principal components of log(layer + small_count)
+        (``phases.py:307-383``): optional robust scaling of the PCs by their 0.5 / 99.5 percentiles around the median, and
+        optional zero at the widest gap of the angle distribution.  ``plot`` is accepted and ignored (no plotting here)."""
+        from sklearn.decomposition import PCA
+
+        if layer not in anndata_object.layers:
+            raise ValueError(f"{layer=} is not a valid entry anndata.obs")
+        sub = anndata_object if genes_to_use is None else anndata_object[:, [g in genes_to_use for g in anndata_object.var.index]]
+        L = sub.layers[layer]
+        L = L.toarray() if hasattr(L, "toarray") else np.asarray(L)
+        X = np.log(L + small_count)                                       # (Nc, Ng)
+        pca = PCA(n_components, random_state=random_state)
+        pcs = pca.fit_transform(X)
+        if normalize_pcs:
+            lo, hi, med = np.percentile(pcs, [0.5, 99.5, 50], 0)
+            pcs = (pcs - med) / (hi - lo)
+        angle = np.arctan2(pcs[:, 1], pcs[:, 0]) % (2 * np.pi)
+        if zero_at_min_density:
+            order = np.argsort(angle)
+            start = order[np.diff(angle[order]).argmax() + 1]
+            angle = (angle - angle[start]) % (2 * np.pi)
+        out = cls()
+        out.phi_xy = pd.DataFrame(np.vstack([np.cos(angle), np.sin(angle)]) * concentration, index=_ROWS,
+                                  columns=anndata_object.obs.index)
+        out.pcs, out.pca = pcs, pca
         return out
 
     # ---- gauge ----------------------------------------------------------------------------------------------
