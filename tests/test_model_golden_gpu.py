@@ -113,6 +113,12 @@ def test_conditioned_velocity_fit_driver_runs_and_matches():
     assert fit.cycle_pyro.disp_pyro.shape == (mp.Ng,)
     assert tuple(fit.phase_pyro.phis.shape) == (mp.Nc,) and float(fit.phase_pyro.phis.min()) >= 0.0
     assert fit.speed_pyro.means.shape == (Kw, mp.Nx) and list(fit.speed_pyro.means.index)[0] == "nu0"
+    # ... and the expected log counts at the fitted parameters (velocity_inference_model.py:232-260)
+    for k in ("ElogS", "ElogU", "ElogS2", "ElogU2"):
+        assert tuple(fit.posterior[k].shape) == (mp.Ng, mp.Nc) and bool(torch.isfinite(fit.posterior[k]).all()), k
+    d = fit.posterior["ElogS"] - fit.posterior["ElogS2"]                     # differs by cf_c - mean(cf) only
+    cf = mp.count_factor.reshape(-1).cpu()
+    assert torch.allclose(d, (cf - cf.mean()).expand_as(d), atol=1e-5)
 
 
 def test_phase_fit_driver_returns_containers():
@@ -132,6 +138,10 @@ def test_phase_fit_driver_returns_containers():
     assert fit.cycle_pyro.disp_pyro.shape == (mp.Ng,)
     assert fit.phase_pyro.phi_xy.shape == (2, mp.Nc)
     assert np.array_equal(fit.phase_pyro.phi_xy_tensor.numpy(), fit.phis_pyro.astype(np.float32))
+    assert tuple(fit.posterior["ElogS"].shape) == (mp.Ng, mp.Nc) and "ElogS2" in fit.posterior and "ElogU" not in fit.posterior
+    fit.max_dense_elements = 0                                              # the dense summaries are optional
+    fit.fit(ClippedAdam({"lr": 0.03, "betas": (0.8, 0.99)}), num_steps=2, verbose=False)
+    assert "ElogS" not in fit.posterior and "ν" in fit.posterior
 
 
 @pytest.mark.parametrize("kind", ["phase", "velocity", "velocity_lrmn"])

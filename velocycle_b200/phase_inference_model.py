@@ -74,6 +74,8 @@ class PhaseFitModel:
     Plotting is not part of this package: ``verbose`` only logs.
     """
 
+    max_dense_elements = 200_000_000  # (Ng x Nc) above which fit() does not materialise ElogS / ElogS2
+
     def __init__(self, metaparams, condition_on={}, early_exit=False, get_posterior=True, num_samples=500, n_per_bin=50):
         _, _, poutine, _, _ = backend.get()
         if len(condition_on) == 0:
@@ -132,6 +134,15 @@ class PhaseFitModel:
             rs = ["ν", "ϕxy", "ϕ", "ζ", "shape_inv"] + (["Δν"] if self.metaparams.with_delta_nu else [])
             bins = [self.sample_posterior(num_samples=self.n_per_bin, rs=rs) for _ in range(nbins)]
             self.posterior = {k: torch.vstack([b[k] for b in bins]) for k in bins[0]}
+            # expected log counts at the fitted parameters (phase_inference_model.py:241-256), on the CPU like the reference;
+            # skipped above max_dense_elements: each is a dense (Ng, Nc) matrix
+            if mp.Ng * mp.Nc <= self.max_dense_elements:
+                from .posterior import expected_log_counts_summary
+
+                nu = pyro.param("ν_locs").detach().cpu().reshape(mp.Ng, -1)
+                dnu = pyro.param("Δν_locs").detach().cpu().reshape(mp.Nb, mp.Ng) if mp.with_delta_nu else None
+                bid = packed_counts_for(mp, need_U=False).batch_id.cpu() if mp.with_delta_nu else None
+                self.posterior.update(expected_log_counts_summary(nu, self.phase_pyro.phis, mp.count_factor.detach().cpu(), dnu, bid))
         if store_output:
             return intermediate_output
 

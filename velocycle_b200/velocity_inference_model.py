@@ -91,6 +91,8 @@ def velocity_latent_variable_model_LRMN(mp, init_loc_fn=None):
 class VelocityFitModel:
     """Fit driver with the reference's constructor and ``fit`` signature (``velocity_inference_model.py:32-153``)."""
 
+    max_dense_elements = 200_000_000  # (Ng x Nc) above which fit() does not materialise ElogS / ElogU (+ the averaged pair)
+
     def __init__(self, metaparams, condition_on={}, early_exit=False, get_posterior=True, num_samples=500, n_per_bin=50):
         _, _, poutine, _, _ = backend.get()
         if len(condition_on) == 0:
@@ -179,6 +181,21 @@ class VelocityFitModel:
                 self.cycle_pyro.set_log_gammas(self.log_gammas)
                 self.speed_pyro = AngularSpeed.from_array(condition_names=conds, means_array=self.velocity_coef.squeeze(),
                                                           stds_array=self.velocity_coef_sd.squeeze(), Nhω=mp.Nhω)
+            # expected log counts at the fitted parameters / posterior means (velocity_inference_model.py:232-260), on the CPU
+            # like the reference; skipped above max_dense_elements: each of the four is a dense (Ng, Nc) matrix
+            if mp.Ng * mp.Nc <= self.max_dense_elements:
+                from .likelihood import packed_counts_for
+                from .posterior import expected_log_counts_summary
+
+                pc = packed_counts_for(mp, need_U=True)
+                nu = pyro.param("ν_locs").detach().cpu().reshape(mp.Ng, -1)
+                dnu = pyro.param("Δν_locs").detach().cpu().reshape(mp.Nb, mp.Ng) if mp.with_delta_nu else None
+                cid = pc.cond_id.cpu() if pc.cond_id is not None else torch.zeros(mp.Nc, dtype=torch.int32)
+                velo = dict(nu_omega=self.posterior["νω"].mean(0).reshape(mp.Nx, mp.Nhω), cond_id=cid,
+                            gamma=self.posterior["γg"].mean(0).reshape(-1), logbeta=self.posterior["logβg"].mean(0).reshape(-1))
+                self.posterior.update(expected_log_counts_summary(
+                    nu, self.phase_pyro.phis, mp.count_factor.detach().cpu(), dnu,
+                    pc.batch_id.cpu() if mp.with_delta_nu else None, velocity=velo))
         if store_output:
             return intermediate_output
 
