@@ -156,6 +156,8 @@ def _sparse_matrix(lam, Nc, ld, seed=0):
 
 @pytest.mark.parametrize("lam,shape,fmt", [(0.4, (3000, 2000), _lib.VCB_COUNTS_B2N), (2.0, (777, 52), _lib.VCB_COUNTS_B2N),
                                            (3.7, (4100, 200), _lib.VCB_COUNTS_B4), (0.4, (1, 4), _lib.VCB_COUNTS_B2),
+                                           (0.9, (70001, 8), _lib.VCB_COUNTS_B2N),   # two packing chunks: nibble carry, ragged tail
+                                           (3.7, (70001, 8), _lib.VCB_COUNTS_B4),
                                            (400.0, (300, 40), _lib.VCB_COUNTS_I32)])
 def test_sub_byte_format_choice_and_host_packing(lam, shape, fmt):
     M = _sparse_matrix(lam, *shape)

@@ -1,4 +1,5 @@
-"""Timing of the fused step at one size with the tcgen05 kernel (VCB_UMMA_DEBUG experiments from the environment)."""
+"""Timing of the fused step at one size with the tcgen05 kernel.  The VCB_UMMA_DEBUG / VCB_UMMA_TRACE experiments of DESIGN.md
+section 4c need a library built with -DVCB_UMMA_INSTRUMENT (both vcb.cu and vcb_umma.cu); the product build ignores them."""
 import os, sys
 os.environ.setdefault("VCB_STREAM_KERNEL", "umma")
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
