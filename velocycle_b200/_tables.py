@@ -96,10 +96,11 @@ class CoefficientTables:
         pd.concat([self.means, self.stds]).to_csv(pathname)
 
     # ---- growing / shrinking --------------------------------------------------------------------------------
-    def extend(self, names: Sequence[str], means=0.0, stds=None) -> None:
-        """Append columns (genes / conditions) filled with ``means`` / ``stds`` (in place)."""
+    def extend(self, gene_names: Sequence[str], means=0.0, stds=None) -> None:
+        """Append columns filled with ``means`` / ``stds`` (in place).  The parameter is called ``gene_names`` in both of the
+        reference's classes (``cycle.py:200``, ``angularspeed.py:157``), also where the columns are conditions."""
         stds = self._default_extension_std if stds is None else stds
-        extra = self.trivial_prior(names, harmonics=self.harmonics, means=means, stds=stds)
+        extra = self.trivial_prior(gene_names, harmonics=self.harmonics, means=means, stds=stds)
         self.means = pd.concat([self.means, extra.means], axis=1)
         self.stds = pd.concat([self.stds, extra.stds], axis=1)
 

@@ -24,7 +24,7 @@ from .velocity_inference_guide import velocity_latent_variable_guide, velocity_l
 from .velocity_inference_model import velocity_latent_variable_model, velocity_latent_variable_model_LRMN
 
 __all__ = [
-    "make_design_matrix", "make_phase_metaparams", "make_velocity_metaparams",
+    "make_design_matrix", "make_phase_metaparams", "make_velocity_metaparams", "filter_shared_genes",
     "preprocess_for_phase_estimation", "preprocess_for_velocity_estimation", "count_factor_from_totals",
 ]
 
@@ -46,6 +46,28 @@ def make_design_matrix(anndata, ids="batch") -> torch.Tensor:
     levels: dict = {}
     codes = np.array([levels.setdefault(v, len(levels)) for v in np.asarray(anndata.obs[ids])])
     return torch.nn.functional.one_hot(torch.as_tensor(codes), len(levels)).to(torch.int64)
+
+
+def filter_shared_genes(cycle, data, filter_type: str = "intersection"):
+    """Restrict a Cycle prior and an AnnData-like object to a common gene set, SORTED by gene name
+    (``preprocessing.py:20-63``).  ``intersection``: genes present in both; ``union``: every gene of the data (all genes of the
+    Cycle must be in the data), the Cycle extended with uninformative entries (means 0, stds 10) for the new ones."""
+    from .cycle import Cycle, reorder
+
+    cycle_genes, data_genes = set(cycle.genes), set(data.var.index)
+    if filter_type == "intersection":
+        keep = np.array(sorted(cycle_genes & data_genes))
+        return Cycle.from_array(means_array=cycle.means[keep], stds_array=cycle.stds[keep]), data[:, keep].copy()
+    if filter_type == "union":
+        if cycle_genes - data_genes:
+            raise Exception("Gene features detected in Cycle object cannot be found in AnnData object")
+        keep = np.array(sorted(cycle_genes | data_genes))
+        new_cycle = Cycle.from_array(means_array=cycle.means, stds_array=cycle.stds)
+        extra = np.array(sorted(data_genes - cycle_genes))
+        if extra.size:
+            new_cycle.extend(gene_names=extra)
+        return reorder(new_cycle, keep), data[:, keep].copy()
+    raise Exception(f"{filter_type=} is not a supported gene filtering behavior")
 
 
 def count_factor_from_totals(S_totals: torch.Tensor) -> torch.Tensor:
@@ -185,12 +207,19 @@ def preprocess_for_phase_estimation(
         raise ValueError("the B200 path implements the NegativeBinomial noise model on raw integer counts")
     S = _counts_layer(anndata.layers["spliced"])
     U = _counts_layer(anndata.layers["unspliced"])
-    return make_phase_metaparams(
+    mp = make_phase_metaparams(
         S, U, cycle_obj.means_tensor.T, cycle_obj.stds_tensor.T, phase_obj.phi_xy_tensor.T,
         batch_id=_ids_from_design(design_mtx), Nb=int(np.asarray(design_mtx).shape[-1]), n_harmonics=n_harmonics,
         with_delta_nu=with_delta_nu, μΔν=μΔν, σΔν=σΔν, gamma_alpha=gamma_alpha, gamma_beta=gamma_beta, device=device,
         cycle_prior=cycle_obj, phase_prior=phase_obj,
     )
+    # the remaining fields of the reference's container (preprocessing.py:168-203), laid out as the reference lays them out;
+    # the dense (Ng, Nc) logS / logU matrices (used by the Lognormal variants and by plotting only) are not materialised
+    d = mp._asdict()
+    d["count_factor"] = mp.count_factor.reshape(1, 1, mp.Nc)
+    d["condition"] = np.array(list(condition_on.keys()))
+    d["beta0"], d["beta1"] = torch.tensor(beta0).to(device), torch.tensor(beta1).to(device)
+    return _container(d)
 
 
 def preprocess_for_velocity_estimation(
@@ -209,10 +238,12 @@ def preprocess_for_velocity_estimation(
         raise ValueError(f"{gene_selection_model=} is not a valid model")
     if noisemodel != "NegativeBinomial" or normalize:
         raise ValueError("the B200 path implements the NegativeBinomial noise model on raw integer counts")
+    if hasattr(anndata, "var") and getattr(cycle_obj, "means", None) is not None and cycle_obj.means.columns is not None:
+        cycle_obj, anndata = filter_shared_genes(cycle_obj, anndata, filter_type=behavior)   # preprocessing.py:246
     S = _counts_layer(anndata.layers["spliced"])
     U = _counts_layer(anndata.layers["unspliced"])
     cf = count_factor if isinstance(count_factor, torch.Tensor) else None
-    return make_velocity_metaparams(
+    mp = make_velocity_metaparams(
         S, U, cycle_obj.means_tensor.T, cycle_obj.stds_tensor.T, phase_obj.phi_xy_tensor.T,
         speed_obj.means_tensor.T, speed_obj.stds_tensor.T,
         batch_id=_ids_from_design(batch_design_mtx), cond_id=_ids_from_design(condition_design_mtx),
@@ -222,3 +253,10 @@ def preprocess_for_velocity_estimation(
         gamma_beta=gamma_beta, rho_mean=rho_mean, rho_std=rho_std, rho_scale=rho_scale, rho_rank=rho_rank,
         device=device, cycle_prior=cycle_obj, phase_prior=phase_obj, speed_prior=speed_obj,
     )
+    # the remaining fields of the reference's container (preprocessing.py:270-322); logS / logU as in the phase stage
+    d = mp._asdict()
+    if cf is not None:
+        d["count_factor"] = cf.clone().detach().to(device)          # passed through in the caller's shape, like the reference
+    d["ν"] = cycle_obj.means_tensor.T.unsqueeze(-2).to(device)
+    d["condition"] = np.array(list(condition_on.keys()))
+    return _container(d)
