@@ -177,3 +177,18 @@ def test_phases_from_pca_heuristic(gold):
         assert p.pcs.shape == (60, 2) and list(p.phi_xy.columns)[:2] == ["k0", "k1"]
     with pytest.raises(ValueError):
         Phases.from_pca_heuristic(ad, layer="nope")
+
+
+def test_circular_corrcoef():
+    from velocycle_b200.utils import circular_corrcoef
+
+    rng = np.random.default_rng(0)
+    a = rng.uniform(0, 2 * np.pi, 500)
+    assert abs(circular_corrcoef(a, a) - 1.0) < 1e-12
+    assert abs(circular_corrcoef(a, (a + 1.234) % (2 * np.pi)) - 1.0) < 1e-12        # invariant to a common rotation
+    assert circular_corrcoef(a, rng.uniform(0, 2 * np.pi, 500)) < 0.15
+    ref = np.abs(np.mean(np.exp(1j * a) * np.conj(np.exp(1j * (a + 0.3 * rng.normal(size=500))))))   # the reference's expression
+    rng = np.random.default_rng(0); a = rng.uniform(0, 2 * np.pi, 500); b = a + 0.3 * np.random.default_rng(5).normal(size=500)
+    assert abs(circular_corrcoef(a, b) - np.abs(np.mean(np.exp(1j * a) * np.conj(np.exp(1j * b))))) < 1e-12
+    with pytest.raises(AssertionError):
+        circular_corrcoef(a, a[:10])

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import torch
 
-__all__ = ["torch_fourier_basis", "torch_basis", "pack_direction", "unpack_direction"]
+__all__ = ["torch_fourier_basis", "torch_basis", "pack_direction", "unpack_direction", "circular_corrcoef"]
 
 
 def torch_fourier_basis(ϕ: torch.Tensor, num_harmonics: int, der: int = 0, device=None) -> torch.Tensor:
@@ -46,3 +46,13 @@ def unpack_direction(loc: torch.Tensor, concentration: float = 1.0) -> torch.Ten
 
 def pack_direction(xy_pair: torch.Tensor) -> torch.Tensor:
     return torch.atan2(xy_pair[..., 1], xy_pair[..., 0])
+
+
+def circular_corrcoef(x1, x2) -> float:
+    """|mean(exp(i (x1 - x2)))|: 1 when two sets of angles agree up to a common rotation (``utils.py:586-611``); the figure
+    of merit for inferred phases against ground truth."""
+    import numpy as np
+
+    x1, x2 = np.asarray(x1, dtype=np.float64), np.asarray(x2, dtype=np.float64)
+    assert len(x1) == len(x2), "Input arrays must have the same length"
+    return float(np.abs(np.mean(np.exp(1j * (x1 - x2)))))
