@@ -20,6 +20,18 @@
 // genes 4grp + j -- and the cells q, q+4: one LDS.128 per cell and matrix brings its counts, and the register pairs the
 // tensor memory load returns are gene pairs, so all fp32 math is packed f32x2 without a single register move.
 //
+// Roles and synchronisation (mbarriers only; one __syncthreads at setup and one at teardown).
+//   16 compute warps   wait fwd_full[b] -> tcgen05.ld {y', d, e} -> cp.async.wait (their own count ring: a warp loads exactly
+//                      the 32 genes x 8 cells x {S, U} per chunk it consumes) -> add up cell `warp` of chunk ci-2 from the
+//                      parked partial sums -> element math -> tcgen05.st the g / w hi | lo planes into G[b] -> park this
+//                      chunk's per-cell sums -> arrive g_full[b] -> refill the count slot.  (fwd(ci) is issued behind
+//                      bwd(ci-2), so fwd_full[b] also says that G[b] and the parked sums of chunk ci-2 are free / complete.)
+//   producer warp      bulk-copies the forward / backward table tiles of chunk ti into 8-deep rings as soon as the MMAs of
+//                      chunk ti-8 have released the slot (tcgen05.commit -> tabf_free / tabb_free).
+//   MMA warp           converged, one elected lane issues: fwd(0), fwd(1); then per chunk: wait g_full[b] -> bwd(ci) (16
+//                      TS MMAs) -> commit bwd_done[b], tabb_free -> fwd(ci+2) (6 SS MMAs) -> commit fwd_full[b], tabf_free.
+//   D_fwd and G are double-buffered in TMEM (b = ci & 1); TMEM is full: 192 + 256 + 64 = 512 columns.
+//
 // Precision.  Inputs: x = hi + lo with hi = rna_tf32(x) for the tables and nu (once per step) and hi = trunc(x) for
 // the per-element gradients; the hardware truncates lo to TF32: 2^-21 relative per product.  Accumulation: the
 // forward accumulator starts from zero every chunk; the backward accumulators are drained into fp32 global sums
