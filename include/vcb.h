@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define VCB_VERSION 110 /* 0.1.1 */
+#define VCB_VERSION 200 /* 0.2.0 */
 
 #define VCB_MAX_HARMONICS 5 /* gene / angular-speed harmonics compiled in: H in 0..5 */
 
@@ -57,6 +57,9 @@ extern "C" {
 #define VCB_FLAG_TCGEN05 4u       /* stream with the tcgen05 kernel (vcb_umma.cuh) where it applies: velocity model, VCB_FLAG_GRAD,
                                      no VCB_FLAG_LGAMMA_INLINE, H <= 3, Nb <= 1; ignored otherwise.  Same results to fp32 rounding;
                                      the environment variable VCB_STREAM_KERNEL=umma turns it on for every call */
+
+#define VCB_FLAG_LEGACY_STREAM 8u  /* stream with the round-1 kernel (vcb_stream.cuh) even where the round-2 kernel applies
+                                     (kept for A/B measurements and as the H > 3 / inline-lgamma path) */
 
 /* error codes (negative) */
 #define VCB_OK 0

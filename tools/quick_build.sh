@@ -6,6 +6,7 @@ F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -
 objs=${@:-vcb vcb_umma}
 for o in $objs; do
   case $o in
+    vcb_stream2_h*) h=${o#vcb_stream2_h}; nvcc $F -DVCB_INST_H=$h -c -o build/obj/$o.o velocycle_b200/csrc/vcb_stream2_inst.cu & ;;
     vcb_stream_h*) h=${o#vcb_stream_h}; nvcc $F -DVCB_INST_H=$h -c -o build/obj/$o.o velocycle_b200/csrc/vcb_stream_inst.cu & ;;
     *) nvcc $F -c -o build/obj/$o.o velocycle_b200/csrc/$o.cu & ;;
   esac

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvcb.so")
 VCB_FLAG_GRAD = 1
 VCB_FLAG_LGAMMA_INLINE = 2
 VCB_FLAG_TCGEN05 = 4
+VCB_FLAG_LEGACY_STREAM = 8
 VCB_MAX_HARMONICS = 5
 VCB_COUNTS_U8, VCB_COUNTS_U16, VCB_COUNTS_I32 = 1, 2, 4
 VCB_CSR_F32, VCB_CSR_I32, VCB_CSR_F64, VCB_CSR_I64 = 0, 1, 2, 3

@@ -10,6 +10,7 @@
 
 #include "vcb_common.cuh"
 #include "vcb_stream.cuh"
+#include "vcb_stream2.cuh"
 #include "vcb_umma.cuh"
 
 #ifndef VCB_DEFAULT_NP
@@ -33,6 +34,8 @@ struct CellParams {
   float* tab;
   long long Nc, n_groups;
   int H, Hw, Nx, velo, tabg;
+  int v2;  // tables for vcb_stream2.cuh: omega * ln2 in the tail, backward sections as {Zhi, Zhi, Zlo, Zlo} TF32 pairs,
+           // slot 16 of the first group of every 16-cell stage = the stage's batch (or -1)
 };
 
 constexpr int kCellEpiThreads = 256;
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
     // eta = -3e4 so that all its terms vanish; backward it collects sum_c w = d/dgamma
     v[0][lane][K] = valid ? (P.cf ? P.cf[c] : 0.f) : -30000.f;  // (inside the FP16 range of the cross-term operand)
     v[4][lane][K] = 1.f;
-    s_tail[warp][lane] = omega;
+    s_tail[warp][lane] = P.v2 ? omega * kLn2 : omega;
     s_tail[warp][8 + lane] = __int_as_float(P.batch_id ? P.batch_id[cl] : 0);
   }
   __syncwarp();
@@ -99,6 +102,11 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
   // one table entry: {TF32 hi of the main MMA's b0, b1; 16-bit pairs {y0, y1} and {lo y0, lo y1} of the cross-term
   // MMA: FP16 for the forward sections, BF16 for the backward ones (see mma_split_fwd / mma_split_bwd)}
   auto emit = [&](int sec_out, int ks, bool f16, float x0, float x1, float y0, float y1) {
+    if (P.v2 && !f16) {  // 3xTF32 backward operand: hi and lo parts of the same two values
+      out[(sec_out * KS + ks) * 32 + lane] = make_float4(__uint_as_float(tf32_rna(x0)), __uint_as_float(tf32_rna(x1)),
+                                                         tf32_lo(x0), tf32_lo(x1));
+      return;
+    }
     const uint32_t c0 = f16 ? pack_f16(y0, y1) : pack_bf16(y0, y1);
     const uint32_t c1 = f16 ? pack_f16(tf32_lo(y0), tf32_lo(y1)) : pack_bf16(tf32_lo(y0), tf32_lo(y1));
     out[(sec_out * KS + ks) * 32 + lane] = make_float4(__uint_as_float(tf32_rna(x0)), __uint_as_float(tf32_rna(x1)),
@@ -129,6 +137,13 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
     int b = __float_as_int(s_tail[warp][8]);
     for (int i = 1; i < kGroupCells; ++i)
       if (__float_as_int(s_tail[warp][8 + i]) != b) b = -1;
+    if (P.v2 && P.batch_id != nullptr) {  // the whole 16-cell stage must agree (padding cells copy the last cell)
+      const long long c0 = (group & ~1ll) * kGroupCells;
+      for (int i = 0; i < s2::kStageCells; ++i) {
+        const long long c = c0 + i < P.Nc ? c0 + i : P.Nc - 1;
+        if (P.batch_id[c] != b) b = -1;
+      }
+    }
     s_tail[warp][16] = __int_as_float(b);
     s_tail[warp][17] = s_tail[warp][18] = s_tail[warp][19] = 0.f;
   }
@@ -150,6 +165,7 @@ struct CellEpiParams {
   double* dnw_part;  // [gridDim.x][Nx*Kw] per-block partial sums of d/dnu_omega (summed in order by the gene epilogue)
   long long Nc, Ncp;
   int n_part, NQ, Hw, Nx;
+  float scale;  // vcb_stream2 accumulates d/dphi and d/domega against log2(e)-scaled contractions: ln 2 here, else 1
 };
 
 __global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
@@ -165,6 +181,8 @@ __global__ void vcb_cell_epilogue_kernel(const CellEpiParams P) {
     float q[3] = {0.f, 0.f, 0.f};
     for (int t = 0; t < P.n_part; ++t)
       for (int i = 0; i < P.NQ; ++i) q[i] += P.cellpart[((long long)t * P.Ncp + c) * P.NQ + i];
+    q[1] *= P.scale;
+    q[2] *= P.scale;
     float dphi = q[1];
     if (velo) {
       phi = P.phi[c];
@@ -233,6 +251,8 @@ struct GeneEpiParams {
   int n_split, H, Nb, Nx, Hw;
   int velo, grad, lginline;
   int dnu_rows;  // single batch, d/ddnu = the constant column of d/dnu (tcgen05 path): no atomics buffer
+  int v2;        // partial rows written by vcb_stream2: ROW_AS / ROW_AU already hold the -r L terms, ROW_LS = sum(LS + LU);
+                 // dnu_acc = per-split batch sums [n_split][Nb][ld] (the constant column of ROW_DNU is then zero)
 };
 
 constexpr int kEpiGenes = 8;
@@ -283,6 +303,24 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
     }
     __syncthreads();
   }
+  // vcb_stream2: d/dDelta-nu[b][g] = fixed-order sum of the per-split batch sums; their total is d/dnu_0
+  double dnu0_v2 = 0.0;
+  if (P.v2 && P.grad && P.Nb > 0 && P.dnu_acc != nullptr) {
+    for (int b = 0; b < P.Nb; ++b) {
+      double s = 0.0;
+      if (valid)
+        for (int sidx = ly; sidx < P.n_split; sidx += kEpiLanes) s += (double)P.dnu_acc[((long long)sidx * P.Nb + b) * P.ld + g];
+      s_part[ly][gx] = s;
+      __syncthreads();
+      if (ly == 0 && valid) {
+        double t = 0.0;
+        for (int l = 0; l < kEpiLanes; ++l) t += s_part[l][gx];
+        dnu0_v2 += t;
+        if (P.d_dnu) P.d_dnu[(long long)b * P.Ng + g] = (float)t;
+      }
+      __syncthreads();
+    }
+  }
   double r = 1.0;
   if (valid) r = 1.0 / (double)P.shape_inv[g];
   {
@@ -312,18 +350,20 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
     }
     // the streaming kernel works in units of mu/r: LS = sum lg2(1 + mu/r), so n r log r has already cancelled
     const double AS = s_rows[ROW_AS][gx] * kLn2d, LS = s_rows[ROW_LS][gx] * kLn2d;
-    const double lpS = AS - r * LS + lgS;
+    const double lpS = P.v2 ? AS + lgS : AS - r * LS + lgS;
     P.lp_S[g] = (float)lpS;
     double LU = 0.0;
     if (P.velo) {
       const double AU = s_rows[ROW_AU][gx] * kLn2d;
-      LU = s_rows[ROW_LU][gx] * kLn2d;
-      P.lp_U[g] = (float)(AU - r * LU + lgU);
+      if (!P.v2) LU = s_rows[ROW_LU][gx] * kLn2d;
+      P.lp_U[g] = (float)(P.v2 ? AU + lgU : AU - r * LU + lgU);
     }
     if (P.grad) {
       double dnu0 = s_rows[ROW_DNU][gx];
       if (P.dnu_rows) {
         if (P.d_dnu) P.d_dnu[g] = (float)dnu0;
+      } else if (P.v2 && P.Nb > 0 && P.dnu_acc != nullptr) {
+        dnu0 = dnu0_v2;
       } else if (P.Nb > 0 && P.dnu_acc != nullptr) {
         dnu0 = 0.0;
         for (int b = 0; b < P.Nb; ++b) {
@@ -605,17 +645,21 @@ struct Plan {
   int smem;
 };
 
+// SM count of the CURRENT device (asked every call: a process may drive several GPUs); 148 on a B200
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      n = v;
-    else
-      n = 148;
-  }
-  return n;
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+      v > 0)
+    return v;
+  return 148;
+}
+
+// VCB_OK when the current device can run the sm_100a code in this library
+static int check_device() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return VCB_ERR_DEVICE;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return VCB_ERR_DEVICE;
+  return major == 10 ? VCB_OK : VCB_ERR_DEVICE;
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -678,6 +722,55 @@ static Plan make_plan(const vcb_problem_t* p, bool velo) {
   off = align_up(off + (size_t)pl.n_tiles * pl.NQ * pl.Ncp * 4, 256);
   pl.off_dnuacc = off;
   off = align_up(off + (size_t)(p->Nb > 0 ? p->Nb : 0) * p->Ng * 4, 256);
+  pl.off_dnwpart = off;
+  pl.n_cell_blocks = (int)((p->Nc + kCellEpiThreads - 1) / kCellEpiThreads);
+  off = align_up(off + (size_t)(pl.n_cell_blocks > 0 ? pl.n_cell_blocks : 1) * (p->Nx > 0 ? p->Nx : 1) * (2 * p->Hw + 1) * 8, 256);
+  pl.total = off;
+  return pl;
+}
+
+// ---- round-2 streaming kernel (vcb_stream2.cuh): every call without inline lgamma and with H <= 3 ----------------------
+struct Plan2 {
+  int n_tiles, n_split, n_ring, tabg, rows, NQ, smem, n_cell_blocks;
+  long long n_stages, n_groups, Ncp;
+  size_t off_tab, off_genepart, off_cellpart, off_dnupart, off_dnwpart, total;
+};
+
+static bool stream2_applies(const vcb_problem_t* p) {
+  return !(p->flags & (VCB_FLAG_LGAMMA_INLINE | VCB_FLAG_LEGACY_STREAM)) && ksteps(p->H) == 1 && p->Nc > 0;
+}
+
+static Plan2 make_plan2(const vcb_problem_t* p, bool velo) {
+  Plan2 pl{};
+  constexpr int tile_g = 32 * (s2::kThreads / 32);
+  pl.n_tiles = (int)((p->ld + tile_g - 1) / tile_g);
+  if (pl.n_tiles < 1) pl.n_tiles = 1;
+  pl.n_stages = (p->Nc + s2::kStageCells - 1) / s2::kStageCells;
+  pl.n_groups = pl.n_stages * s2::kGPS;
+  pl.Ncp = pl.n_stages * s2::kStageCells;
+  long long ns = (long long)sm_count() / pl.n_tiles;
+  if (ns > pl.n_stages) ns = pl.n_stages;
+  if (ns < 1) ns = 1;
+  pl.n_split = (int)ns;
+  pl.tabg = table_group_floats(p->H, velo);
+  pl.rows = gene_rows(p->H);
+  pl.NQ = velo ? 3 : 2;
+  pl.n_ring = 2;
+  for (int r = s2::kMaxNS; r >= 2; --r)
+    if (s2::smem_layout(p->H, velo, s2::kThreads / 32, r).total <= kSmemBudget - 1024) {
+      pl.n_ring = r;
+      break;
+    }
+  pl.smem = s2::smem_layout(p->H, velo, s2::kThreads / 32, pl.n_ring).total;
+  size_t off = 0;
+  pl.off_tab = off;
+  off = align_up(off + (size_t)pl.n_groups * pl.tabg * 4, 256);
+  pl.off_genepart = off;
+  off = align_up(off + (size_t)pl.n_split * pl.rows * p->ld * 4, 256);
+  pl.off_cellpart = off;
+  off = align_up(off + (size_t)pl.n_tiles * pl.NQ * pl.Ncp * 4, 256);
+  pl.off_dnupart = off;
+  off = align_up(off + (size_t)pl.n_split * (p->Nb > 0 ? p->Nb : 0) * p->ld * 4, 256);
   pl.off_dnwpart = off;
   pl.n_cell_blocks = (int)((p->Nc + kCellEpiThreads - 1) / kCellEpiThreads);
   off = align_up(off + (size_t)(pl.n_cell_blocks > 0 ? pl.n_cell_blocks : 1) * (p->Nx > 0 ? p->Nx : 1) * (2 * p->Hw + 1) * 8, 256);
@@ -774,6 +867,24 @@ VCB_DECL_LAUNCH(4)
 VCB_DECL_LAUNCH(5)
 #undef VCB_DECL_LAUNCH
 
+#define VCB_DECL_LAUNCH2(h) \
+  cudaError_t vcb_launch_stream2_h##h(bool velo, bool grad, const s2::Params& sp, dim3 grid, int nthr, int smem, cudaStream_t st);
+VCB_DECL_LAUNCH2(0)
+VCB_DECL_LAUNCH2(1)
+VCB_DECL_LAUNCH2(2)
+VCB_DECL_LAUNCH2(3)
+#undef VCB_DECL_LAUNCH2
+
+static cudaError_t launch_stream2(int H, bool velo, bool grad, const s2::Params& sp, dim3 grid, int smem, cudaStream_t st) {
+  switch (H) {
+    case 0: return vcb_launch_stream2_h0(velo, grad, sp, grid, s2::kThreads, smem, st);
+    case 1: return vcb_launch_stream2_h1(velo, grad, sp, grid, s2::kThreads, smem, st);
+    case 2: return vcb_launch_stream2_h2(velo, grad, sp, grid, s2::kThreads, smem, st);
+    case 3: return vcb_launch_stream2_h3(velo, grad, sp, grid, s2::kThreads, smem, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 static cudaError_t launch_stream(int H, bool velo, bool grad, bool lgi, int np, const StreamParams& sp, dim3 grid,
                                  int nthr, int smem, cudaStream_t st) {
   switch (H) {
@@ -846,7 +957,7 @@ static int run_umma(const vcb_problem_t* p, void* workspace, size_t ws_bytes, vo
   }
   {
     CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
-                     dnw_part, p->Nc,  pl.Ncp, pl.n_tiles, 3, p->Hw, p->Nx};
+                     dnw_part, p->Nc,  pl.Ncp, pl.n_tiles, 3, p->Hw, p->Nx, 1.f};
     const int bs = kCellEpiThreads;
     const size_t sm = (size_t)(bs / 32) * p->Nx * (2 * p->Hw + 1) * 8;
     vcb_cell_epilogue_kernel<<<(unsigned)pl.n_cell_blocks, bs, sm, st>>>(ce);
@@ -889,11 +1000,100 @@ static int run_umma(const vcb_problem_t* p, void* workspace, size_t ws_bytes, vo
   return VCB_OK;
 }
 
+static unsigned event_flags(cudaStream_t st) {  // timing events inside a stream capture must become event-record NODES
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) return cudaEventRecordExternal;
+  return cudaEventRecordDefault;
+}
+
+// table kernel -> vcb_stream2 -> cell epilogue -> gene epilogue
+static int run2(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_bytes, void* stream) {
+  const Plan2 pl = make_plan2(p, velo);
+  if (ws_bytes < pl.total) return VCB_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool grad = (p->flags & VCB_FLAG_GRAD) != 0;
+  unsigned char* ws = (unsigned char*)workspace;
+  float* tab = (float*)(ws + pl.off_tab);
+  float* genepart = (float*)(ws + pl.off_genepart);
+  float* cellpart = (float*)(ws + pl.off_cellpart);
+  float* dnupart = (grad && p->Nb > 0) ? (float*)(ws + pl.off_dnupart) : nullptr;
+  double* dnw_part = (double*)(ws + pl.off_dnwpart);
+  cudaError_t e;
+  if (dnupart) {
+    e = cudaMemsetAsync(dnupart, 0, (size_t)pl.n_split * p->Nb * p->ld * 4, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    CellParams cp{p->phi, p->cf, p->Nb > 0 ? p->batch_id : nullptr, p->cond_id, velo ? p->nu_omega : nullptr,
+                  tab,    p->Nc, pl.n_groups, p->H, p->Hw, p->Nx, velo ? 1 : 0, pl.tabg, 1};
+    vcb_cell_tables_kernel<<<(unsigned)((pl.n_groups + kTabWarps - 1) / kTabWarps), kTabWarps * 32, 0, st>>>(cp);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    s2::Params sp{p->S,    velo ? p->U : nullptr, tab,      p->nu,    p->Nb > 0 ? p->dnu : nullptr, p->shape_inv, p->logbeta,
+                  p->gamma, genepart,              cellpart, dnupart,  p->Nc,                        p->Ng,        p->ld,
+                  pl.Ncp,  pl.n_stages,            pl.n_split, p->Nb, pl.n_ring};
+    dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.n_split);
+    const unsigned ev_flags = (p->ev_stream_begin || p->ev_stream_end) ? event_flags(st) : 0u;
+    if (p->ev_stream_begin) cudaEventRecordWithFlags((cudaEvent_t)p->ev_stream_begin, st, ev_flags);
+    e = launch_stream2(p->H, velo, grad, sp, grid, pl.smem, st);
+    if (e != cudaSuccess) return (int)e;
+    if (p->ev_stream_end) cudaEventRecordWithFlags((cudaEvent_t)p->ev_stream_end, st, ev_flags);
+  }
+  if (grad) {
+    CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
+                     dnw_part, p->Nc,  pl.Ncp, pl.n_tiles, pl.NQ, p->Hw, velo ? p->Nx : 0, kLn2};
+    const int bs = kCellEpiThreads;
+    const size_t sm = velo ? (size_t)(bs / 32) * p->Nx * (2 * p->Hw + 1) * 8 : 0;
+    vcb_cell_epilogue_kernel<<<(unsigned)pl.n_cell_blocks, bs, sm, st>>>(ce);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    GeneEpiParams ge{};
+    ge.genepart = genepart;
+    ge.shape_inv = p->shape_inv;
+    ge.dnu_acc = dnupart;
+    ge.dnw_part = dnw_part;
+    ge.n_cell_blocks = grad ? pl.n_cell_blocks : 0;
+    ge.spec_S = p->spec_S;
+    ge.spec_U = p->spec_U;
+    ge.lp_S = p->lp_S;
+    ge.lp_U = p->lp_U;
+    ge.d_nu = p->d_nu;
+    ge.d_dnu = p->d_dnu;
+    ge.d_shape_inv = p->d_shape_inv;
+    ge.d_logbeta = p->d_logbeta;
+    ge.d_gamma = p->d_gamma;
+    ge.d_nu_omega = p->d_nu_omega;
+    ge.Nc = p->Nc;
+    ge.Ng = p->Ng;
+    ge.ld = p->ld;
+    ge.n_split = pl.n_split;
+    ge.H = p->H;
+    ge.Nb = p->Nb;
+    ge.Nx = p->Nx;
+    ge.Hw = p->Hw;
+    ge.velo = velo;
+    ge.grad = grad;
+    ge.lginline = 0;
+    ge.v2 = 1;
+    vcb_gene_epilogue_kernel<<<(unsigned)((p->Ng + kEpiGenes - 1) / kEpiGenes), kEpiGenes * kEpiLanes, 0, st>>>(ge);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return VCB_OK;
+}
+
 static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_bytes, void* stream) {
   int rc = validate(p, velo);
   if (rc != VCB_OK) return rc;
   if (workspace == nullptr) return VCB_ERR_NULL;
   if (((uintptr_t)workspace & 15) != 0) return VCB_ERR_ALIGN;
+  rc = check_device();
+  if (rc != VCB_OK) return rc;
+  if (!(p->flags & VCB_FLAG_TCGEN05) && stream2_applies(p)) return run2(p, velo, workspace, ws_bytes, stream);
   if ((stream_kernel_choice() == 1 || (p->flags & VCB_FLAG_TCGEN05)) && umma_applies(p, velo)) return run_umma(p, workspace, ws_bytes, stream);
   const Plan pl = make_plan(p, velo);
   if (ws_bytes < pl.total) return VCB_ERR_WORKSPACE;
@@ -916,7 +1116,7 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
   }
   if (p->Nc > 0) {
     CellParams cp{p->phi, p->cf, p->Nb > 0 ? p->batch_id : nullptr, p->cond_id, velo ? p->nu_omega : nullptr,
-                  tab,    p->Nc, pl.n_groups, p->H, p->Hw, p->Nx, velo ? 1 : 0, pl.tabg};
+                  tab,    p->Nc, pl.n_groups, p->H, p->Hw, p->Nx, velo ? 1 : 0, pl.tabg, 0};
     vcb_cell_tables_kernel<<<(unsigned)((pl.n_groups + kTabWarps - 1) / kTabWarps), kTabWarps * 32, 0, st>>>(cp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -925,7 +1125,7 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
     StreamParams sp{p->S,     velo ? p->U : nullptr, tab,   p->nu,  p->Nb > 0 ? p->dnu : nullptr,
                     p->shape_inv, p->logbeta,        p->gamma, genepart, cellpart,
                     dnu_acc,  p->Nc,                 p->Ng, p->ld,  pl.Ncp, pl.n_split,
-                    p->Nb, pl.n_ring, getenv("VCB_DEBUG_SKIP_COMPUTE") != nullptr ? 1 : 0};
+                    p->Nb, pl.n_ring};
     dim3 grid((unsigned)pl.n_tiles, (unsigned)pl.n_split);
     // timing events: inside a stream capture they must become event-record NODES (external flag)
     unsigned ev_flags = cudaEventRecordDefault;
@@ -941,7 +1141,7 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
   }
   if (grad && p->Nc > 0) {
     CellEpiParams ce{cellpart, p->phi, p->cond_id, p->nu_omega, p->d_phi, p->d_cf, p->d_omega,
-                     dnw_part, p->Nc,  pl.Ncp, pl.n_tiles, pl.NQ, p->Hw, velo ? p->Nx : 0};
+                     dnw_part, p->Nc,  pl.Ncp, pl.n_tiles, pl.NQ, p->Hw, velo ? p->Nx : 0, 1.f};
     const int bs = kCellEpiThreads;
     const size_t sm = velo ? (size_t)(bs / 32) * p->Nx * (2 * p->Hw + 1) * 8 : 0;
     vcb_cell_epilogue_kernel<<<(unsigned)pl.n_cell_blocks, bs, sm, st>>>(ce);
@@ -1013,6 +1213,10 @@ size_t vcb_workspace_bytes(const vcb_problem_t* p) {
       p->Hw > VCB_MAX_HARMONICS)
     return 0;
   size_t n = vcb::make_plan(p, p->U != nullptr).total;
+  if (vcb::stream2_applies(p)) {
+    const size_t m2 = vcb::make_plan2(p, p->U != nullptr).total;
+    if (m2 > n) n = m2;
+  }
   if (p->U != nullptr && p->H <= 3 && p->Nb <= 1 && p->Nc > 0) {  // either streaming kernel may serve the call
     const size_t m = vcb::make_plan_umma(p).total;
     if (m > n) n = m;

@@ -84,7 +84,6 @@ struct StreamParams {
   int n_split;
   int Nb;
   int n_ring;              // depth of the table ring
-  int debug_skip_compute;  // profiling aid: stream the tiles but skip the arithmetic
 };
 
 struct StreamSmem {
@@ -116,9 +115,15 @@ __device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+#ifdef VCB_EXP_NOMUFU
+__device__ __forceinline__ float2 ex2_2(float2 a) { return f2(a.x * 0.001f + 1.f, a.y * 0.001f + 1.f); }
+__device__ __forceinline__ float2 lg2_2(float2 a) { return f2(a.x * 0.5f - 0.5f, a.y * 0.5f - 0.5f); }
+__device__ __forceinline__ float2 rcp_2(float2 a) { return f2(2.f - a.x, 2.f - a.y); }
+#else
 __device__ __forceinline__ float2 ex2_2(float2 a) { return f2(ex2_approx(a.x), ex2_approx(a.y)); }
 __device__ __forceinline__ float2 lg2_2(float2 a) { return f2(lg2_approx(a.x), lg2_approx(a.y)); }
 __device__ __forceinline__ float2 rcp_2(float2 a) { return f2(rcp_approx(a.x), rcp_approx(a.y)); }
+#endif
 
 // ---- cp.async (LDGSTS.128): 16 bytes global -> shared, zero-filled when src_bytes == 0 ---------------------------
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
@@ -653,7 +658,7 @@ __global__ void __launch_bounds__(max_threads(NPAIR), 1) vcb_stream_kernel(const
     const float4* cnt = s_cnt + (size_t)c_d * NLD * nthr;
     float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
 
-    if (!P.debug_skip_compute) {
+    {
       // batch bookkeeping (CTA-uniform decisions: every warp reads the same table)
       bool mixed = false;
       if (P.Nb > 0) {

@@ -1,0 +1,626 @@
+// The streaming kernel, second generation (round 2): same mapping and arithmetic as vcb_stream.cuh -- one pass over
+// the [cells][genes] count tiles of S (and U) that yields the per-gene log-prob partial sums AND every gradient
+// partial sum, contractions on the tensor pipe, counts through a warp-private cp.async ring, operand tables staged
+// by the TMA engine -- rebuilt around the round-1 profile (profiles/r01_stream_kernel_ncu_summary.txt): that kernel
+// was issue bound, 475 warp instructions per warp and 8-cell group of which ~190 were bookkeeping.  What changed:
+//
+//   * a ring stage is TWO 8-cell groups (16 cells): one table copy, one full[] wait, one done[] arrival, one batch
+//     test and one issue test per 16 cells;
+//   * the table ring is refilled by a fixed rotation with a blocking wait on a stage that is already one stage old
+//     (the issuer of stage st retires stage st-1), instead of three non-blocking polls per group in every warp;
+//   * nu, the constant term and the size-factor slot are pre-scaled by log2(e) in the A operands, omega by ln 2 in the
+//     table, so the MMA result IS the base-2 exponent; the relu offset 1e-5 rides gamma: m = max(a + eps, eps);
+//   * the backward operands use the 3xTF32 form  G.Z ~ Ghi.Zhi + Ghi.Zlo + Glo.Zhi  with Ghi = G & ~0x1fff and
+//     Glo = G - Ghi passed as raw fp32: 6 instructions per operand and row tile instead of 10 (no 16-bit packing),
+//     one more MMA on a tensor pipe that was 20 % busy;
+//   * per-cell sums (d/dphi, d/dcf, d/domega) are accumulated per cell in scalar registers straight from the
+//     accumulator fragments: no re-pairing moves;
+//   * batch offsets: cells arrive sorted by batch and padded to whole stages (PackedCounts does that once per
+//     dataset), d/dDelta-nu of a (split, batch, gene) is written by the one thread that owns the gene: no atomics,
+//     bit-reproducible.  A stage whose 16 cells disagree (a C-ABI caller with unsorted ids) is processed once per
+//     batch present with the other cells masked out -- slow, correct and still deterministic;
+//   * no debug branches, no NPAIR / inline-lgamma variants (those calls keep using vcb_stream.cuh).
+#pragma once
+#include "vcb_stream.cuh"
+
+namespace vcb {
+namespace s2 {
+
+constexpr int kGPS = 2;                          // 8-cell groups per ring stage
+constexpr int kStageCells = kGPS * kGroupCells;  // 16
+constexpr int kD = 4;                            // count groups in flight per warp (two stages)
+constexpr int kMaxNS = 8;                        // table-ring depth limit (mbarrier slots)
+constexpr int kThreads = 512;
+constexpr int kHeader = 256;
+constexpr float kRelEps = 1e-5f;
+
+struct Params {
+  const float* S;
+  const float* U;
+  const float* tab;  // [n_stages_total][kGPS][table_group_floats]
+  const float* nu;
+  const float* dnu;
+  const float* shape_inv;
+  const float* logbeta;
+  const float* gamma;
+  float* genepart;  // [n_split][rows][ld]
+  float* cellpart;  // [n_tiles][Ncp][NQ]
+  float* dnupart;   // [n_split][Nb][ld], zeroed by the caller; (split, gene) has exactly one writer
+  long long Nc, Ng, ld, Ncp;
+  long long n_stages_total;
+  int n_split;
+  int Nb;
+  int n_ring;
+};
+
+struct Smem {
+  int part_off, gene_off, aop_off, tab_off, cnt_off, total;
+};
+
+__host__ __device__ inline Smem smem_layout(int H, bool velo, int nwarps, int n_ring) {
+  Smem L;
+  int off = kHeader;
+  L.part_off = off;  // cell partials: [park slot][group][warp][quantity][cell], park ring = table ring + 2 stages
+  off += (n_ring + 2) * kGPS * nwarps * (velo ? 3 : 2) * 8 * 4;
+  L.gene_off = off;  // per-gene parameters: [warp][row tile][2][grp] float4
+  off += nwarps * 2 * 2 * 8 * 16;
+  L.aop_off = off;  // forward A operands: [warp][row tile][k-step][main / cross][lane] uint4
+  off += nwarps * 2 * ksteps(H) * 2 * 32 * 16;
+  L.tab_off = off;
+  off += n_ring * kGPS * table_group_floats(H, velo) * 4;
+  off = (off + 127) / 128 * 128;
+  L.cnt_off = off;  // [depth][matrix][cell q / q+4][thread] x 16 B
+  off += kD * (velo ? 2 : 1) * 2 * (32 * nwarps) * 16;
+  L.total = off;
+  return L;
+}
+
+template <int H, bool VELO, bool GRAD>
+__global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P) {
+  constexpr int K = 2 * H + 1;
+  constexpr int KS = ksteps(H);
+  constexpr int NT = 2;  // MMA row tiles per warp (32 genes)
+  constexpr int NMAT = VELO ? 2 : 1;
+  constexpr int NQ = VELO ? 3 : 2;
+  constexpr int R = kGroupCells;
+  constexpr int D = kD;
+  constexpr int NLD = NMAT * 2;
+  constexpr int TABG = table_group_floats(H, VELO);
+  constexpr int TAIL = table_tail(H, VELO);
+  constexpr bool NEED_D = GRAD || VELO;
+  constexpr bool NEED_E = GRAD && VELO;
+  constexpr uint32_t kStageTabBytes = (uint32_t)(kGPS * TABG * 4);
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  constexpr int nthr = kThreads, nwarps = nthr >> 5;
+  constexpr uint32_t kSlotBytes = (uint32_t)nthr * 16u;  // distance between two of a thread's count slots
+  const int warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, q = lane & 3;
+  const int NS = P.n_ring;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  constexpr int tile_genes = 32 * nwarps;
+  const long long g_base = (long long)tile * tile_genes;
+  const long long rem = P.ld - g_base;
+  const int W = (int)(rem < (long long)tile_genes ? rem : (long long)tile_genes);
+  const Smem L = smem_layout(H, VELO, nwarps, NS);
+  const uint32_t full0 = smem_u32(smem_raw);
+  const uint32_t done0 = full0 + 8 * kMaxNS;
+  float* const s_part = reinterpret_cast<float*>(smem_raw + L.part_off);
+  float* const s_tab = reinterpret_cast<float*>(smem_raw + L.tab_off);
+
+  // this CTA's stages
+  const long long T0 = (P.n_stages_total * split) / P.n_split;
+  const long long T1 = (P.n_stages_total * (split + 1)) / P.n_split;
+  const int n_stages = (int)(T1 - T0);
+  const long long G0 = T0 * kGPS;  // first 8-cell group
+
+  // ---- per-gene constants -> shared memory ---------------------------------------------------------------
+  // gene j in 0..3 of the lane: g = g_base + warp*32 + 4*grp + j; row tile mt = j>>1 holds it in fragment row grp (j even)
+  // or grp+8 (j odd).
+  const int gl = warp * 32 + 4 * grp;
+  const bool gvalid = gl < W;
+  auto gene_of = [&](int mt, int odd) -> long long { return g_base + gl + 2 * mt + odd; };
+  auto a_value = [&](long long g, int slot) -> float {  // forward A operand, already in base-2 units
+    if (g >= P.Ng || slot == 0 || slot > K) return 0.f;
+    return slot == K ? kLog2e : P.nu[g * K + slot] * kLog2e;
+  };
+  auto const_term = [&](long long g, int b) -> float {  // (nu_0 - ln r + batch offset) log2 e; a padding gene contributes nothing
+    if (g >= P.Ng) return -1e30f;
+    float v = P.nu[g * K] + logf(P.shape_inv[g]);
+    if (b >= 0) v += P.dnu[(long long)b * P.Ng + g];
+    return v * kLog2e;
+  };
+  uint4* const s_aop = reinterpret_cast<uint4*>(smem_raw + L.aop_off) + (size_t)warp * (NT * KS * 2 * 32) + lane;
+  float4* const s_gene = reinterpret_cast<float4*>(smem_raw + L.gene_off) + (size_t)warp * (NT * 2 * 8) + grp;
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t am[4], ax[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) am[i] = tf32_rna(a_value(gene_of(mt, i & 1), 8 * ks + q + 4 * (i >> 1)));
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const float x0 = a_value(gene_of(mt, o), 8 * ks + 2 * q), x1 = a_value(gene_of(mt, o), 8 * ks + 2 * q + 1);
+        ax[o] = pack_f16(tf32_lo(x0), tf32_lo(x1));
+        ax[2 + o] = pack_f16(x0, x1);
+      }
+      s_aop[((mt * KS + ks) * 2 + 0) * 32] = make_uint4(am[0], am[1], am[2], am[3]);
+      s_aop[((mt * KS + ks) * 2 + 1) * 32] = make_uint4(ax[0], ax[1], ax[2], ax[3]);
+    }
+    if (q == 0) {
+      float rs[2], gs[2], ibs[2];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const long long g = gene_of(mt, o);
+        const bool ok = g < P.Ng;
+        rs[o] = ok ? 1.0f / P.shape_inv[g] : 1.f;
+        gs[o] = ((ok && VELO) ? P.gamma[g] : 1.f) + kRelEps;
+        ibs[o] = (ok && VELO) ? expf(-P.logbeta[g]) : 1.f;
+      }
+      s_gene[(mt * 2 + 0) * 8] = make_float4(-rs[0], -rs[1], const_term(gene_of(mt, 0), -1), const_term(gene_of(mt, 1), -1));
+      s_gene[(mt * 2 + 1) * 8] = make_float4(gs[0], gs[1], ibs[0], ibs[1]);
+    }
+  }
+  __syncwarp();
+  auto set_batch = [&](int b) {
+    __syncwarp();
+    if (q == 0) {
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt) {
+        float4 v = s_gene[(mt * 2 + 0) * 8];
+        v.z = const_term(gene_of(mt, 0), b);
+        v.w = const_term(gene_of(mt, 1), b);
+        s_gene[(mt * 2 + 0) * 8] = v;
+      }
+    }
+    __syncwarp();
+  };
+  int cur_b = -1;
+
+  const float2 zero2 = f2s(0.f);
+  float2 accAS[NT], accL[NT], accAU[NT], accGU[NT];  // AS / AU already hold the -r L terms; L = LS + LU feeds d/dr
+  float accNu[NT][KS][4];
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt) {
+    accAS[mt] = accL[mt] = accAU[mt] = accGU[mt] = zero2;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) accNu[mt][ks][i] = 0.f;
+  }
+  // batch boundary: the constant column of d/dnu (slot 0: lanes q == 0, c0 / c2) is the batch's d/dDelta-nu.  Every
+  // (split, gene) has exactly one owner, so a plain read-modify-write is race free and the result reproducible.
+  auto flush_batch = [&]() {
+    if (q == 0 && cur_b >= 0) {
+#pragma unroll
+      for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const long long g = gene_of(mt, o);
+          if (g < P.ld) {
+            float* dst = P.dnupart + ((long long)split * P.Nb + cur_b) * P.ld + g;
+            *dst += accNu[mt][0][2 * o];
+          }
+          accNu[mt][0][2 * o] = 0.f;
+        }
+    }
+  };
+
+  // ---- count ring: warp-private cp.async pipeline (layout and loader mapping as in vcb_stream.cuh) -----------
+  // Loader lane (row l_row = lane/8 of each half group, 16-byte chunk lane%8) copies into the slot of the lane that will
+  // consume the data.  Rows outside the matrix and gene chunks past the row pitch are zero-filled by the copy itself
+  // (src-size 0: nothing is read, so the source address needs no clamping): `rows_left` counts the matrix rows from this
+  // lane's row of the next group on, and is pinned to 0 for a lane without genes.
+  const int l_row = lane >> 3, l_chunk = lane & 7;
+  // Slot of (row r in 0..3, 16-byte gene chunk c in 0..7) inside a warp's 512-byte block: r*8 + (c ^ 2r).  A loader quarter-warp
+  // (one row, chunks 0..7) and a consumer quarter-warp (rows 0..3 x two chunks) both touch eight different 16-byte bank
+  // groups: neither the copy's shared-memory write nor the consumer's LDS.128 has a bank conflict.  (With the plain
+  // consumer-order layout the copy wrote at a 64-byte stride: a 4-way conflict on every LDGSTS.)
+#ifdef VCB_EXP_NOSWZ
+  const uint32_t s_cnt_ld = smem_u32(reinterpret_cast<float4*>(smem_raw + L.cnt_off) + (warp * 32 + 4 * l_chunk + l_row));
+#else
+  const uint32_t s_cnt_ld = smem_u32(reinterpret_cast<float4*>(smem_raw + L.cnt_off) + (warp * 32 + l_row * 8 + (l_chunk ^ (2 * l_row))));
+#endif
+  const int lgl = warp * 32 + 4 * l_chunk;
+  const char* ldS;
+  long long u_minus_s = 0;
+  int rows_left;
+  {
+    const long long off = (G0 * R + l_row) * P.ld + g_base + lgl;
+    ldS = reinterpret_cast<const char*>(P.S + off);
+    if (VELO) u_minus_s = reinterpret_cast<const char*>(P.U) - reinterpret_cast<const char*>(P.S);
+    const long long c_end = T1 * kStageCells < P.Nc ? T1 * kStageCells : P.Nc;  // this CTA's rows end here
+    long long rl = c_end - (G0 * R + l_row);
+    rl = rl < 0 ? 0 : (rl > (1ll << 30) ? (1ll << 30) : rl);
+    rows_left = lgl < W ? (int)rl : 0;
+  }
+  auto load_counts = [&](int d) {  // the next group (in order) into depth slot d; past the CTA's range the copies are all zero-fill
+    uint32_t dst = s_cnt_ld + (uint32_t)d * (NLD * kSlotBytes);
+    const uint32_t sz0 = rows_left > 0 ? 16u : 0u, sz1 = rows_left > 4 ? 16u : 0u;
+    const char* hi = ldS + 16 * P.ld;  // row r + 4
+    cp_async16(dst, ldS, sz0);
+    cp_async16(dst + kSlotBytes, hi, sz1);
+    if (VELO) {
+      cp_async16(dst + 2 * kSlotBytes, ldS + u_minus_s, sz0);
+      cp_async16(dst + 3 * kSlotBytes, hi + u_minus_s, sz1);
+    }
+    ldS += 4ll * R * P.ld;
+    rows_left = rows_left > R ? rows_left - R : 0;
+    cp_async_commit();
+  };
+
+  // ---- table ring ------------------------------------------------------------------------------------------
+  //   full[s] : mbarrier, the two operand tables of the stage in slot s have landed  (arrive.expect_tx + complete_tx)
+  //   done[s] : plain counter of the warps that have finished with slot s (tables and parked cell partials)
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 8 * s), "r"(0u) : "memory");
+    }
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 8 * kMaxNS), "r"(0u) : "memory");
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue_stage = [&](int stage, int slot) {  // one elected lane
+    mbar_expect_tx(full0 + 8 * slot, kStageTabBytes);
+    bulk_g2s(smem_u32(s_tab) + (uint32_t)slot * kStageTabBytes, P.tab + (T0 + stage) * (long long)(kGPS * TABG), kStageTabBytes,
+             full0 + 8 * slot);
+  };
+  if (tid == 0)
+    for (int s = 0; s < NS && s < n_stages; ++s) issue_stage(s, s);
+  float* const cellpart_t = P.cellpart + (long long)tile * P.Ncp * NQ;
+  // Cell partials of a group: a warp reduces its NQ x 8 per-cell sums over its 32 genes (three shuffle levels) and parks
+  // them; stage x is drained -- the 16 warps' terms added in a fixed order (deterministic) and stored -- by warp
+  // x % nwarps after that warp has left stage x + 1, by which time every warp has long left stage x (`completed` says
+  // so; the wait is a formality).  The park ring is two stages deeper than the table ring, which keeps any warp from
+  // re-using a park slot before its drainer has passed (a warp can be at most NS - 1 stages ahead of the slowest one).
+  const int NP = NS + 2;
+  const uint32_t completed_addr = done0 + 8 * kMaxNS;  // number of stages every warp has left (monotonic)
+  auto flush_partials = [&](int stage) {
+    {
+      uint32_t spins = 0, c;
+      do {
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(c) : "r"(completed_addr) : "memory");
+        if (++spins > (1u << 24)) __trap();
+      } while ((int)c <= stage);
+    }
+    if (lane < R * NQ) {
+      const int i = lane >> 3, cell = lane & 7;
+      const int pslot = stage % NP;
+#pragma unroll
+      for (int h = 0; h < kGPS; ++h) {
+        const float* src = s_part + (size_t)(pslot * kGPS + h) * nwarps * (NQ * 8) + lane;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < nwarps; ++w) s += src[w * (NQ * 8)];
+        cellpart_t[((T0 + stage) * kGPS + h) * (R * NQ) + cell * NQ + i] = s;
+      }
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < D; ++s) load_counts(s);
+
+  const float2 one2 = f2s(1.f), neg1 = f2s(-1.f), eps2 = f2s(kRelEps);
+  #ifdef VCB_EXP_NOSWZ
+  const float4* const s_cnt = reinterpret_cast<const float4*>(smem_raw + L.cnt_off) + tid;
+#else
+  const float4* const s_cnt = reinterpret_cast<const float4*>(smem_raw + L.cnt_off) + (warp * 32 + q * 8 + (grp ^ (2 * q)));
+#endif
+
+  // One 8-cell group of one batch.  MASKED: compile-time copy used for stages whose cells belong to several batches;
+  // cells outside batch `pass_b` are switched off (their counts read as zero, their exponent as -inf).
+  auto process = [&](auto masked_tag, const float* tb, const float4* cnt, const int pass_b, float (&pcf)[2], float (&pphi)[2],
+                     float (&pom)[2]) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
+    const float4* tb4 = reinterpret_cast<const float4*>(tb);
+    float om[2] = {0.f, 0.f};
+    if (VELO) {
+      om[0] = tb[TAIL + q];
+      om[1] = tb[TAIL + q + 4];
+    }
+    float moff[2] = {0.f, 0.f}, mk[2] = {1.f, 1.f};
+    if (MASKED) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const bool in = __float_as_int(tb[TAIL + 8 + q + 4 * cc]) == pass_b;
+        moff[cc] = in ? 0.f : -60000.f;
+        mk[cc] = in ? 1.f : 0.f;
+      }
+    }
+    float2 pcf2[2] = {zero2, zero2};
+    const float2* cnt2 = reinterpret_cast<const float2*>(cnt);
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+      // ---- forward contractions: y (base-2 exponent without the constant), d log2e, omega d'' log2e ----------
+      float Ce[4] = {0.f, 0.f, 0.f, 0.f}, Cd[4] = {0.f, 0.f, 0.f, 0.f}, Cw[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint4 a0 = s_aop[((mt * KS + ks) * 2 + 0) * 32], a1 = s_aop[((mt * KS + ks) * 2 + 1) * 32];
+        const uint32_t am[4] = {a0.x, a0.y, a0.z, a0.w}, ax[4] = {a1.x, a1.y, a1.z, a1.w};
+#ifdef VCB_EXP_NOFWD
+        Ce[0] = __uint_as_float(am[0]) * tb[q]; Ce[1] = __uint_as_float(am[1]) * tb[q]; Ce[2] = __uint_as_float(am[2]) * tb[q]; Ce[3] = __uint_as_float(am[3]) * tb[q];
+        Cd[0] = __uint_as_float(ax[0]) * tb[q]; Cd[1] = __uint_as_float(ax[1]) * tb[q]; Cd[2] = __uint_as_float(ax[2]) * tb[q]; Cd[3] = __uint_as_float(ax[3]) * tb[q];
+        Cw[0] = Ce[1]; Cw[1] = Cd[2]; Cw[2] = Ce[3]; Cw[3] = Cd[0];
+#else
+        mma_split_fwd(Ce, am, ax, tb4[(SEC_F0 * KS + ks) * 32 + lane]);
+        if (NEED_D) mma_split_fwd(Cd, am, ax, tb4[(SEC_F1 * KS + ks) * 32 + lane]);
+        if (NEED_E) mma_split_fwd(Cw, am, ax, tb4[(SEC_F2 * KS + ks) * 32 + lane]);
+#endif
+      }
+      const float4 ga = s_gene[(mt * 2 + 0) * 8];
+      const float2 nr_mt = f2(ga.x, ga.y);
+      float2 gam_mt = one2, invb_mt = one2;
+      if (VELO) {
+        const float4 gb = s_gene[(mt * 2 + 1) * 8];
+        gam_mt = f2(gb.x, gb.y);
+        invb_mt = f2(gb.z, gb.w);
+      }
+      float2 Gg[2], Gw[2];
+#ifdef VCB_EXP_NOELEM
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const float2 kS = cnt2[((size_t)cc * nthr) * 2 + mt], kU = cnt2[((size_t)(2 + cc) * nthr) * 2 + mt];
+        Gg[cc] = add2(f2(Ce[cc], Ce[2 + cc]), kS);
+        Gw[cc] = add2(f2(Cd[cc] + Cw[cc], Cd[2 + cc] + Cw[2 + cc]), kU);
+        accAS[mt] = add2(accAS[mt], Gg[cc]);
+        pcf[cc] += Gw[cc].x;
+      }
+      if (false)
+#endif
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        float2 kS = cnt2[((size_t)cc * nthr) * 2 + mt];
+        float2 kU = VELO ? cnt2[((size_t)(2 + cc) * nthr) * 2 + mt] : kS;
+        float2 y = f2(Ce[cc] + ga.z, Ce[2 + cc] + ga.w);
+        if (MASKED) {
+          y = add2(y, f2s(moff[cc]));
+          kS = mul2(kS, f2s(mk[cc]));
+          kU = mul2(kU, f2s(mk[cc]));
+        }
+        const float2 u = ex2_2(y);
+        const float2 s = add2(u, one2);
+        const float2 LS = lg2_2(s);
+        accAS[mt] = fma2(kS, fma2(LS, neg1, y), accAS[mt]);
+        accAS[mt] = fma2(nr_mt, LS, accAS[mt]);
+        accL[mt] = add2(accL[mt], LS);
+        float2 g = zero2, w = zero2;
+        if (VELO) {
+          const float2 a = f2(fmaf(Cd[cc], om[cc], gam_mt.x), fmaf(Cd[2 + cc], om[cc], gam_mt.y));  // a + eps
+          const float2 m = f2(fmaxf(a.x, kRelEps), fmaxf(a.y, kRelEps));
+          const float2 mb = mul2(m, invb_mt);
+          const float2 uU = mul2(u, mb);
+          const float2 sU = add2(uU, one2);
+          const float2 LU = lg2_2(sU);
+          const float2 lmb = lg2_2(mb);
+          accAU[mt] = fma2(kU, fma2(LU, neg1, add2(y, lmb)), accAU[mt]);
+          accAU[mt] = fma2(nr_mt, LU, accAU[mt]);
+          accL[mt] = add2(accL[mt], LU);
+          if (GRAD) {
+            const float2 sUm = mul2(sU, m);
+            const float2 rc = rcp_2(mul2(s, sUm));  // one MUFU for 1/s and 1/(sU m)
+            const float2 inv_s = mul2(rc, sUm), inv_sUm = mul2(rc, s);
+            const float2 gS = mul2(fma2(nr_mt, u, kS), inv_s);
+            const float2 w0 = mul2(fma2(nr_mt, uU, kU), inv_sUm);
+            const float2 gU = mul2(w0, m);
+            w = mul2(w0, f2(a.x > kRelEps ? 1.f : 0.f, a.y > kRelEps ? 1.f : 0.f));
+            g = add2(gS, gU);
+            accGU[mt] = add2(accGU[mt], gU);
+            pom[cc] = fmaf(w.x, Cd[cc], pom[cc]);
+            pom[cc] = fmaf(w.y, Cd[2 + cc], pom[cc]);
+            pphi[cc] = fmaf(w.x, Cw[cc], pphi[cc]);
+            pphi[cc] = fmaf(w.y, Cw[2 + cc], pphi[cc]);
+          }
+        } else if (GRAD) {
+          g = mul2(fma2(nr_mt, u, kS), rcp_2(s));
+        }
+        if (GRAD) {
+          pcf2[cc] = add2(pcf2[cc], g);
+          pphi[cc] = fmaf(g.x, Cd[cc], pphi[cc]);
+          pphi[cc] = fmaf(g.y, Cd[2 + cc], pphi[cc]);
+        }
+        Gg[cc] = g;
+        Gw[cc] = w;
+      }
+      // ---- backward contractions, 3xTF32: acc[gene][slot] = sum_cells G[gene][cell] Z[cell][slot] ----------------
+#ifdef VCB_EXP_NOBWD
+      if (GRAD) {
+        accNu[mt][0][0] += Gg[0].x + Gw[0].x; accNu[mt][0][1] += Gg[0].y + Gw[0].y; accNu[mt][0][2] += Gg[1].x + Gw[1].x; accNu[mt][0][3] += Gg[1].y + Gw[1].y;
+      }
+      if (false) {
+#else
+      if (GRAD) {
+#endif
+        auto split3 = [&](const float2 v0, const float2 v1, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+          hi[0] = __float_as_uint(v0.x) & 0xffffe000u;
+          hi[1] = __float_as_uint(v0.y) & 0xffffe000u;
+          hi[2] = __float_as_uint(v1.x) & 0xffffe000u;
+          hi[3] = __float_as_uint(v1.y) & 0xffffe000u;
+          const float2 l0 = __fadd2_rn(v0, make_float2(-__uint_as_float(hi[0]), -__uint_as_float(hi[1])));
+          const float2 l1 = __fadd2_rn(v1, make_float2(-__uint_as_float(hi[2]), -__uint_as_float(hi[3])));
+          lo[0] = __float_as_uint(l0.x);
+          lo[1] = __float_as_uint(l0.y);
+          lo[2] = __float_as_uint(l1.x);
+          lo[3] = __float_as_uint(l1.y);
+        };
+        uint32_t gh[4], gl_[4], wh[4], wl[4];
+        split3(Gg[0], Gg[1], gh, gl_);
+        if (VELO) split3(Gw[0], Gw[1], wh, wl);
+#pragma unroll
+        for (int nt = 0; nt < KS; ++nt) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          const float4 bz = tb4[(SEC_B0 * KS + nt) * 32 + lane];  // {Zhi b0, Zhi b1, Zlo b0, Zlo b1}
+          mma_tf32(acc, gl_, __float_as_uint(bz.x), __float_as_uint(bz.y));
+          mma_tf32(acc, gh, __float_as_uint(bz.z), __float_as_uint(bz.w));
+          mma_tf32(acc, gh, __float_as_uint(bz.x), __float_as_uint(bz.y));
+          if (VELO) {
+            const float4 bw = tb4[(SEC_B1 * KS + nt) * 32 + lane];
+            mma_tf32(acc, wl, __float_as_uint(bw.x), __float_as_uint(bw.y));
+            mma_tf32(acc, wh, __float_as_uint(bw.z), __float_as_uint(bw.w));
+            mma_tf32(acc, wh, __float_as_uint(bw.x), __float_as_uint(bw.y));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) accNu[mt][nt][i] += acc[i];
+        }
+      }
+    }
+    if (GRAD) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) pcf[cc] += pcf2[cc].x + pcf2[cc].y;
+    }
+  };
+
+  // ---- main loop ---------------------------------------------------------------------------------------
+  int c_slot = 0, c_phase = 0;  // table slot / parity of the current stage
+  int p_slot = 0;               // park slot of the current stage
+  int drain_next = warp;        // next stage whose parked partials this warp drains
+  for (int st = 0; st < n_stages; ++st) {
+    {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(full0 + 8 * c_slot, (uint32_t)c_phase)) {
+        if (++spins > (1u << 24)) __trap();
+      }
+    }
+    const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
+    const int d0 = (st & 1) * kGPS;
+    const float4* cnt_stage = s_cnt + (size_t)d0 * NLD * nthr;
+    float* part_stage = s_part + ((size_t)p_slot * kGPS * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4));
+
+    int stage_b = 0;
+    if (P.Nb > 0) stage_b = __float_as_int(tb_stage[TAIL + 16]);  // the stage's batch, -1 if its cells disagree
+    if (P.Nb > 0 && stage_b >= 0 && stage_b != cur_b) {
+      if (GRAD) flush_batch();
+      cur_b = stage_b;
+      set_batch(cur_b);
+    }
+#pragma unroll
+    for (int h = 0; h < kGPS; ++h) {
+      cp_async_wait<D - 1>();
+      __syncwarp();
+      const float* tb = tb_stage + h * TABG;
+      const float4* cnt = cnt_stage + (size_t)h * NLD * nthr;
+      float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
+      if (P.Nb > 0 && stage_b < 0) {
+        // mixed stage: one masked pass per batch present among the 16 cells (warp-uniform decisions)
+        const int my_id = __float_as_int(tb_stage[(lane >> 3 & 1) * TABG + TAIL + 8 + (lane & 7)]);
+        for (int b = 0; b < P.Nb; ++b) {
+          if (!__any_sync(0xffffffffu, my_id == b)) continue;
+          if (b != cur_b) {
+            if (GRAD) flush_batch();
+            cur_b = b;
+            set_batch(b);
+          }
+          process(BoolTag<true>{}, tb, cnt, b, pcf, pphi, pom);
+        }
+      } else {
+#ifdef VCB_EXP_NOPROC
+        {
+          const float2* c2 = reinterpret_cast<const float2*>(cnt);
+#pragma unroll
+          for (int j = 0; j < NLD; ++j) {
+            accAS[0] = add2(accAS[0], c2[((size_t)j * nthr) * 2 + 0]);
+            accAS[1] = add2(accAS[1], c2[((size_t)j * nthr) * 2 + 1]);
+          }
+          pcf[0] = tb[q];
+          pphi[0] = tb[TAIL + q];
+        }
+#else
+        process(BoolTag<false>{}, tb, cnt, 0, pcf, pphi, pom);
+#endif
+      }
+      if (GRAD) {
+        // the lane holds partial sums for the cells q and q+4: swap halves so that lanes 0-15 keep cell q and lanes
+        // 16-31 cell q+4, add the four gene groups of each half, and park 8 values per quantity
+        const bool up = (lane & 16) != 0;
+        float v0 = (up ? pcf[1] : pcf[0]) + __shfl_xor_sync(0xffffffffu, up ? pcf[0] : pcf[1], 16);
+        float v1 = (up ? pphi[1] : pphi[0]) + __shfl_xor_sync(0xffffffffu, up ? pphi[0] : pphi[1], 16);
+        float v2 = VELO ? (up ? pom[1] : pom[0]) + __shfl_xor_sync(0xffffffffu, up ? pom[0] : pom[1], 16) : 0.f;
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 4);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 4);
+        if (VELO) v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
+        v0 += __shfl_xor_sync(0xffffffffu, v0, 8);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+        if (VELO) v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
+        if ((lane & 12) == 0) {
+          float* dst = part_stage + h * (nwarps * NQ * 8);
+          dst[0] = v0;
+          dst[8] = v1;
+          if (VELO) dst[16] = v2;
+        }
+      }
+      __syncwarp();           // every lane has read its counts: the slot may be refilled
+      load_counts(d0 + h);
+    }
+    // Leave the stage.  The LAST warp to get here (a shared-memory counter tells) publishes the stage as completed and
+    // refills the table slot with stage st + NS: the refill is issued the moment the slowest warp leaves the stage,
+    // NS - 1 stages before that warp needs it, and nobody waits for anybody.  The drain of the parked partials is a
+    // rotating duty (see flush_partials) so that it never lands on the slowest warp systematically.
+    {
+      if (lane == 0) {
+        uint32_t old;
+        asm volatile("atom.shared.acq_rel.cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(done0 + 8 * c_slot) : "memory");
+        if (old == (uint32_t)(nwarps - 1)) {
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 8 * c_slot), "r"(0u) : "memory");
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(completed_addr), "r"((uint32_t)(st + 1)) : "memory");
+          if (st + NS < n_stages) issue_stage(st + NS, c_slot);
+        }
+      }
+      if (GRAD && st > 0 && drain_next == st - 1) {
+        flush_partials(st - 1);
+        drain_next += nwarps;
+      }
+    }
+    if (++p_slot == NP) p_slot = 0;
+    if (++c_slot == NS) {
+      c_slot = 0;
+      c_phase ^= 1;
+    }
+  }
+  cp_async_wait<0>();
+  if (GRAD) {  // the last stage (no successor) and any stage whose drainer finished early
+    for (; drain_next < n_stages; drain_next += nwarps) flush_partials(drain_next);
+  }
+
+  // ---- flush per-gene partial sums -------------------------------------------------------------------------
+  if (GRAD && P.Nb > 0) flush_batch();
+  constexpr int ROWS = gene_rows(H);
+  float* gp = P.genepart + ((long long)split * ROWS) * P.ld;
+  auto lane_sum4 = [&](float2 v) -> float2 {  // over the 4 lanes (cells) that share a gene pair
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, 1);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, 1);
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, 2);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, 2);
+    return v;
+  };
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt) {
+    const long long g0 = gene_of(mt, 0);
+    auto put = [&](int row, float2 v) {
+      v = lane_sum4(v);
+      if (gvalid && q == 0) *reinterpret_cast<float2*>(gp + (long long)row * P.ld + g0) = v;
+    };
+    put(ROW_AS, accAS[mt]);
+    put(ROW_LS, accL[mt]);
+    if (VELO) {
+      put(ROW_AU, accAU[mt]);
+      if (GRAD) put(ROW_GU, accGU[mt]);
+    }
+    if (GRAD && gvalid) {
+#pragma unroll
+      for (int nt = 0; nt < KS; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int slot_k = 8 * nt + 2 * q + (i & 1);
+          const long long g = g0 + (i >> 1);
+          if (slot_k < K)
+            gp[(long long)(ROW_DNU + slot_k) * P.ld + g] = accNu[mt][nt][i];
+          else if (VELO && slot_k == K)
+            gp[(long long)ROW_W * P.ld + g] = accNu[mt][nt][i];
+        }
+    }
+  }
+}
+
+}  // namespace s2
+}  // namespace vcb

@@ -18,7 +18,8 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import VcbProblem, VcbSpectrum, VCB_FLAG_GRAD, VCB_FLAG_LGAMMA_INLINE, VCB_FLAG_TCGEN05
+from ._lib import (VcbProblem, VcbSpectrum, VCB_FLAG_GRAD, VCB_FLAG_LEGACY_STREAM, VCB_FLAG_LGAMMA_INLINE,
+                   VCB_FLAG_TCGEN05)
 from .sharding import allreduce_flat_
 
 __all__ = ["CountSpectrum", "HostCounts", "PackedCounts", "fused_elbo_grad", "FusedCycleNB", "fused_cycle_nb"]
@@ -495,6 +496,7 @@ def fused_elbo_grad(
     inline_lgamma: bool = False,
     want_d_omega: bool = False,
     tcgen05: bool = False,
+    legacy_stream: bool = False,
 ) -> Dict[str, torch.Tensor]:
     """One launch sequence of the fused path through the C ABI.  All tensors float32 CUDA.
 
@@ -522,7 +524,7 @@ def fused_elbo_grad(
     p = VcbProblem()
     p.Nc, p.Ng, p.ld = Nc, Ng, ld
     p.H, p.Nb = (K - 1) // 2, Nb
-    p.flags = (VCB_FLAG_GRAD if grad else 0) | (VCB_FLAG_LGAMMA_INLINE if inline_lgamma else 0) | (VCB_FLAG_TCGEN05 if tcgen05 else 0)
+    p.flags = (VCB_FLAG_GRAD if grad else 0) | (VCB_FLAG_LGAMMA_INLINE if inline_lgamma else 0) | (VCB_FLAG_TCGEN05 if tcgen05 else 0) | (VCB_FLAG_LEGACY_STREAM if legacy_stream else 0)
     p.S = counts.S.data_ptr()
     p.phi, p.cf = phi.data_ptr(), _ptr(cf)
     p.batch_id = _ptr(counts.batch_id) if Nb > 0 else None
