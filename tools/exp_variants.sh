@@ -1,8 +1,8 @@
 #!/bin/bash
-# build libvcb variants that differ in the H=3 round-2 stream kernel (timing experiments only) into gpurun_out/exp/
+# build libvcb variants that differ in the H=3 round-2 stream kernel (timing experiments only) into tools/exp/
 set -e
 cd "$(dirname "$0")/.."
-mkdir -p gpurun_out/exp
+mkdir -p tools/exp
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -I include -I velocycle_b200/csrc"
 for v in "$@"; do
   flags=""
@@ -13,6 +13,6 @@ done
 wait
 for v in "$@"; do
   objs=$(ls build/obj/*.o | grep -v vcb_stream2_h3.o)
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o gpurun_out/exp/libvcb_$v.so $objs /tmp/exp_$v.o
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o tools/exp/libvcb_$v.so $objs /tmp/exp_$v.o
 done
-ls -la gpurun_out/exp
+ls -la tools/exp

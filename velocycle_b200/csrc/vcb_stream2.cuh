@@ -32,6 +32,11 @@ constexpr int kD = 4;                            // count groups in flight per w
 constexpr int kMaxNS = 8;                        // table-ring depth limit (mbarrier slots)
 constexpr int kThreads = 512;
 constexpr int kHeader = 256;
+#ifdef VCB_EXP_SVC3
+constexpr int kSvcDist = 3;
+#else
+constexpr int kSvcDist = 2;  // a stage is serviced (table slot refilled, parked cell partials drained) this many stages later
+#endif
 constexpr float kRelEps = 1e-5f;
 
 struct Params {
@@ -61,7 +66,7 @@ __host__ __device__ inline Smem smem_layout(int H, bool velo, int nwarps, int n_
   Smem L;
   int off = kHeader;
   L.part_off = off;  // cell partials: [park slot][group][warp][quantity][cell], park ring = table ring + 2 stages
-  off += (n_ring + 2) * kGPS * nwarps * (velo ? 3 : 2) * 8 * 4;
+  off += (n_ring + kSvcDist) * kGPS * nwarps * (velo ? 3 : 2) * 8 * 4;
   L.gene_off = off;  // per-gene parameters: [warp][row tile][2][grp] float4
   off += nwarps * 2 * 2 * 8 * 16;
   L.aop_off = off;  // forward A operands: [warp][row tile][k-step][main / cross][lane] uint4
@@ -177,14 +182,17 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     }
     __syncwarp();
   };
-  int cur_b = -1;
+  // -2 = no batch selected yet (a mixed stage is stamped -1 and must never compare equal); without batches the table kernel
+  // stamps every stage with 0
+  int cur_b = P.Nb > 0 ? -2 : 0;
 
   const float2 zero2 = f2s(0.f);
-  float2 accAS[NT], accL[NT], accAU[NT], accGU[NT];  // AS / AU already hold the -r L terms; L = LS + LU feeds d/dr
+  // per gene pair: sum kS (y - LS), sum LS, sum kU (y + lg2 mb - LU), sum LU, sum gU   (base-2 units; folded at the end)
+  float2 accKS[NT], accLS[NT], accKU[NT], accLU[NT], accGU[NT];
   float accNu[NT][KS][4];
 #pragma unroll
   for (int mt = 0; mt < NT; ++mt) {
-    accAS[mt] = accL[mt] = accAU[mt] = accGU[mt] = zero2;
+    accKS[mt] = accLS[mt] = accKU[mt] = accLU[mt] = accGU[mt] = zero2;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   // batch boundary: the constant column of d/dnu (slot 0: lanes q == 0, c0 / c2) is the batch's d/dDelta-nu.  Every
   // (split, gene) has exactly one owner, so a plain read-modify-write is race free and the result reproducible.
   auto flush_batch = [&]() {
-    if (q == 0 && cur_b >= 0) {
+    if (q == 0 && cur_b >= 0 && P.Nb > 0) {
 #pragma unroll
       for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
@@ -253,13 +261,12 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
 
   // ---- table ring ------------------------------------------------------------------------------------------
   //   full[s] : mbarrier, the two operand tables of the stage in slot s have landed  (arrive.expect_tx + complete_tx)
-  //   done[s] : plain counter of the warps that have finished with slot s (tables and parked cell partials)
+  //   done[s] : mbarrier, every warp has left the stage in slot s (its tables and the parked cell partials are final)
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 8 * s), "r"(0u) : "memory");
+      mbar_init(done0 + 8 * s, nwarps);
     }
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 8 * kMaxNS), "r"(0u) : "memory");
     mbar_fence_init();
   }
   __syncthreads();
@@ -272,31 +279,29 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     for (int s = 0; s < NS && s < n_stages; ++s) issue_stage(s, s);
   float* const cellpart_t = P.cellpart + (long long)tile * P.Ncp * NQ;
   // Cell partials of a group: a warp reduces its NQ x 8 per-cell sums over its 32 genes (three shuffle levels) and parks
-  // them; stage x is drained -- the 16 warps' terms added in a fixed order (deterministic) and stored -- by warp
-  // x % nwarps after that warp has left stage x + 1, by which time every warp has long left stage x (`completed` says
-  // so; the wait is a formality).  The park ring is two stages deeper than the table ring, which keeps any warp from
-  // re-using a park slot before its drainer has passed (a warp can be at most NS - 1 stages ahead of the slowest one).
-  const int NP = NS + 2;
-  const uint32_t completed_addr = done0 + 8 * kMaxNS;  // number of stages every warp has left (monotonic)
-  auto flush_partials = [&](int stage) {
-    {
-      uint32_t spins = 0, c;
-      do {
-        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(c) : "r"(completed_addr) : "memory");
-        if (++spins > (1u << 24)) __trap();
-      } while ((int)c <= stage);
-    }
-    if (lane < R * NQ) {
+  // them, [park slot][warp][quantity][cell][group of the stage].  Stage x is SERVICED by warp (x + 2) % nwarps at the top
+  // of its own stage x + 2: it waits for done[slot of x] (every warp has left stage x -- they are normally long past it, so
+  // the wait returns at once and nobody spins), re-issues the table copy of that slot for stage x + NS, adds the 16 warps'
+  // parked terms in a fixed order (deterministic) and stores them.  A warp can be at most NS - 1 stages ahead of the slowest
+  // one and the servicing warp two stages behind the stage it serves: the park ring has NS + 2 slots.
+  const int NP = NS + kSvcDist;
+  auto service = [&](int x) {
+    const int xs = x % NS;
+    mbar_wait(done0 + 8 * xs, (uint32_t)((x / NS) & 1));
+    if (lane == 0 && x + NS < n_stages) issue_stage(x + NS, xs);
+    if (GRAD && lane < R * NQ) {
       const int i = lane >> 3, cell = lane & 7;
-      const int pslot = stage % NP;
+      const float2* src = reinterpret_cast<const float2*>(s_part) + (size_t)(x % NP) * nwarps * (NQ * 8) + lane;
+      float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int h = 0; h < kGPS; ++h) {
-        const float* src = s_part + (size_t)(pslot * kGPS + h) * nwarps * (NQ * 8) + lane;
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < nwarps; ++w) s += src[w * (NQ * 8)];
-        cellpart_t[((T0 + stage) * kGPS + h) * (R * NQ) + cell * NQ + i] = s;
+      for (int w = 0; w < nwarps; ++w) {
+        const float2 v = src[w * (NQ * 8)];
+        s.x += v.x;
+        s.y += v.y;
       }
+      float* dst = cellpart_t + (T0 + x) * (long long)(kGPS * R * NQ) + cell * NQ + i;
+      dst[0] = s.x;
+      dst[R * NQ] = s.y;
     }
   };
 #pragma unroll
@@ -364,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
         const float2 kS = cnt2[((size_t)cc * nthr) * 2 + mt], kU = cnt2[((size_t)(2 + cc) * nthr) * 2 + mt];
         Gg[cc] = add2(f2(Ce[cc], Ce[2 + cc]), kS);
         Gw[cc] = add2(f2(Cd[cc] + Cw[cc], Cd[2 + cc] + Cw[2 + cc]), kU);
-        accAS[mt] = add2(accAS[mt], Gg[cc]);
+        accKS[mt] = add2(accKS[mt], Gg[cc]);
         pcf[cc] += Gw[cc].x;
       }
       if (false)
@@ -382,9 +387,11 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
         const float2 u = ex2_2(y);
         const float2 s = add2(u, one2);
         const float2 LS = lg2_2(s);
-        accAS[mt] = fma2(kS, fma2(LS, neg1, y), accAS[mt]);
-        accAS[mt] = fma2(nr_mt, LS, accAS[mt]);
-        accL[mt] = add2(accL[mt], LS);
+        accKS[mt] = fma2(kS, fma2(LS, neg1, y), accKS[mt]);
+#ifdef VCB_EXP_OLDACC
+        accKS[mt] = fma2(nr_mt, LS, accKS[mt]);
+#endif
+        accLS[mt] = add2(accLS[mt], LS);
         float2 g = zero2, w = zero2;
         if (VELO) {
           const float2 a = f2(fmaf(Cd[cc], om[cc], gam_mt.x), fmaf(Cd[2 + cc], om[cc], gam_mt.y));  // a + eps
@@ -394,9 +401,13 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
           const float2 sU = add2(uU, one2);
           const float2 LU = lg2_2(sU);
           const float2 lmb = lg2_2(mb);
-          accAU[mt] = fma2(kU, fma2(LU, neg1, add2(y, lmb)), accAU[mt]);
-          accAU[mt] = fma2(nr_mt, LU, accAU[mt]);
-          accL[mt] = add2(accL[mt], LU);
+          accKU[mt] = fma2(kU, fma2(LU, neg1, add2(y, lmb)), accKU[mt]);
+#ifdef VCB_EXP_OLDACC
+          accKU[mt] = fma2(nr_mt, LU, accKU[mt]);
+          accLS[mt] = add2(accLS[mt], LU);
+#else
+          accLU[mt] = add2(accLU[mt], LU);
+#endif
           if (GRAD) {
             const float2 sUm = mul2(sU, m);
             const float2 rc = rcp_2(mul2(s, sUm));  // one MUFU for 1/s and 1/(sU m)
@@ -451,17 +462,19 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
         for (int nt = 0; nt < KS; ++nt) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
           const float4 bz = tb4[(SEC_B0 * KS + nt) * 32 + lane];  // {Zhi b0, Zhi b1, Zlo b0, Zlo b1}
+          // two independent accumulation chains (the g terms and the w terms): a dependent mma.sync costs ~35 cycles, a
+          // single six-deep chain per row tile was 15 % of the kernel
+          float acw[4] = {0.f, 0.f, 0.f, 0.f};
+          float4 bw = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (VELO) bw = tb4[(SEC_B1 * KS + nt) * 32 + lane];
           mma_tf32(acc, gl_, __float_as_uint(bz.x), __float_as_uint(bz.y));
+          if (VELO) mma_tf32(acw, wl, __float_as_uint(bw.x), __float_as_uint(bw.y));
           mma_tf32(acc, gh, __float_as_uint(bz.z), __float_as_uint(bz.w));
+          if (VELO) mma_tf32(acw, wh, __float_as_uint(bw.z), __float_as_uint(bw.w));
           mma_tf32(acc, gh, __float_as_uint(bz.x), __float_as_uint(bz.y));
-          if (VELO) {
-            const float4 bw = tb4[(SEC_B1 * KS + nt) * 32 + lane];
-            mma_tf32(acc, wl, __float_as_uint(bw.x), __float_as_uint(bw.y));
-            mma_tf32(acc, wh, __float_as_uint(bw.z), __float_as_uint(bw.w));
-            mma_tf32(acc, wh, __float_as_uint(bw.x), __float_as_uint(bw.y));
-          }
+          if (VELO) mma_tf32(acw, wh, __float_as_uint(bw.x), __float_as_uint(bw.y));
 #pragma unroll
-          for (int i = 0; i < 4; ++i) accNu[mt][nt][i] += acc[i];
+          for (int i = 0; i < 4; ++i) accNu[mt][nt][i] += VELO ? acc[i] + acw[i] : acc[i];
         }
       }
     }
@@ -474,116 +487,105 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   // ---- main loop ---------------------------------------------------------------------------------------
   int c_slot = 0, c_phase = 0;  // table slot / parity of the current stage
   int p_slot = 0;               // park slot of the current stage
-  int drain_next = warp;        // next stage whose parked partials this warp drains
-  for (int st = 0; st < n_stages; ++st) {
-    {
-      uint32_t spins = 0;
-      while (!mbar_try_wait(full0 + 8 * c_slot, (uint32_t)c_phase)) {
-        if (++spins > (1u << 24)) __trap();
+  // one 8-cell group of the current stage: consume, reduce the per-cell sums over the warp's genes, park them, refill the
+  // count slot
+  auto do_group = [&](auto masked_tag, const int h, const float* tb_stage, const float4* cnt_stage, float* part_stage, const int d0) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
+    cp_async_wait<D - 1>();
+    __syncwarp();
+    const float* tb = tb_stage + h * TABG;
+    const float4* cnt = cnt_stage + (size_t)h * NLD * nthr;
+    float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
+    if (MASKED) {
+      // mixed stage: one masked pass per batch present among the 16 cells (warp-uniform decisions)
+      const int my_id = __float_as_int(tb_stage[(lane >> 3 & 1) * TABG + TAIL + 8 + (lane & 7)]);
+      for (int b = 0; b < P.Nb; ++b) {
+        if (!__any_sync(0xffffffffu, my_id == b)) continue;
+        if (b != cur_b) {
+          if (GRAD) flush_batch();
+          cur_b = b;
+          set_batch(b);
+        }
+        process(BoolTag<true>{}, tb, cnt, b, pcf, pphi, pom);
+      }
+    } else {
+      process(BoolTag<false>{}, tb, cnt, 0, pcf, pphi, pom);
+    }
+    if (GRAD) {
+      // the lane holds partial sums for the cells q and q+4: swap halves so that lanes 0-15 keep cell q and lanes
+      // 16-31 cell q+4, add the four gene groups of each half, and park 8 values per quantity
+      const bool up = (lane & 16) != 0;
+      float v0 = (up ? pcf[1] : pcf[0]) + __shfl_xor_sync(0xffffffffu, up ? pcf[0] : pcf[1], 16);
+      float v1 = (up ? pphi[1] : pphi[0]) + __shfl_xor_sync(0xffffffffu, up ? pphi[0] : pphi[1], 16);
+      float v2 = VELO ? (up ? pom[1] : pom[0]) + __shfl_xor_sync(0xffffffffu, up ? pom[0] : pom[1], 16) : 0.f;
+      v0 += __shfl_xor_sync(0xffffffffu, v0, 4);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 4);
+      if (VELO) v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
+      v0 += __shfl_xor_sync(0xffffffffu, v0, 8);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+      if (VELO) v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
+      if ((lane & 12) == 0) {
+        part_stage[h] = v0;
+        part_stage[16 + h] = v1;
+        if (VELO) part_stage[32 + h] = v2;
       }
     }
-    const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
-    const int d0 = (st & 1) * kGPS;
-    const float4* cnt_stage = s_cnt + (size_t)d0 * NLD * nthr;
-    float* part_stage = s_part + ((size_t)p_slot * kGPS * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4));
-
-    int stage_b = 0;
-    if (P.Nb > 0) stage_b = __float_as_int(tb_stage[TAIL + 16]);  // the stage's batch, -1 if its cells disagree
-    if (P.Nb > 0 && stage_b >= 0 && stage_b != cur_b) {
-      if (GRAD) flush_batch();
-      cur_b = stage_b;
-      set_batch(cur_b);
-    }
-#pragma unroll
-    for (int h = 0; h < kGPS; ++h) {
-      cp_async_wait<D - 1>();
-      __syncwarp();
-      const float* tb = tb_stage + h * TABG;
-      const float4* cnt = cnt_stage + (size_t)h * NLD * nthr;
-      float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
-      if (P.Nb > 0 && stage_b < 0) {
-        // mixed stage: one masked pass per batch present among the 16 cells (warp-uniform decisions)
-        const int my_id = __float_as_int(tb_stage[(lane >> 3 & 1) * TABG + TAIL + 8 + (lane & 7)]);
-        for (int b = 0; b < P.Nb; ++b) {
-          if (!__any_sync(0xffffffffu, my_id == b)) continue;
-          if (b != cur_b) {
-            if (GRAD) flush_batch();
-            cur_b = b;
-            set_batch(b);
-          }
-          process(BoolTag<true>{}, tb, cnt, b, pcf, pphi, pom);
-        }
-      } else {
-#ifdef VCB_EXP_NOPROC
-        {
-          const float2* c2 = reinterpret_cast<const float2*>(cnt);
-#pragma unroll
-          for (int j = 0; j < NLD; ++j) {
-            accAS[0] = add2(accAS[0], c2[((size_t)j * nthr) * 2 + 0]);
-            accAS[1] = add2(accAS[1], c2[((size_t)j * nthr) * 2 + 1]);
-          }
-          pcf[0] = tb[q];
-          pphi[0] = tb[TAIL + q];
-        }
-#else
-        process(BoolTag<false>{}, tb, cnt, 0, pcf, pphi, pom);
-#endif
-      }
-      if (GRAD) {
-        // the lane holds partial sums for the cells q and q+4: swap halves so that lanes 0-15 keep cell q and lanes
-        // 16-31 cell q+4, add the four gene groups of each half, and park 8 values per quantity
-        const bool up = (lane & 16) != 0;
-        float v0 = (up ? pcf[1] : pcf[0]) + __shfl_xor_sync(0xffffffffu, up ? pcf[0] : pcf[1], 16);
-        float v1 = (up ? pphi[1] : pphi[0]) + __shfl_xor_sync(0xffffffffu, up ? pphi[0] : pphi[1], 16);
-        float v2 = VELO ? (up ? pom[1] : pom[0]) + __shfl_xor_sync(0xffffffffu, up ? pom[0] : pom[1], 16) : 0.f;
-        v0 += __shfl_xor_sync(0xffffffffu, v0, 4);
-        v1 += __shfl_xor_sync(0xffffffffu, v1, 4);
-        if (VELO) v2 += __shfl_xor_sync(0xffffffffu, v2, 4);
-        v0 += __shfl_xor_sync(0xffffffffu, v0, 8);
-        v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
-        if (VELO) v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
-        if ((lane & 12) == 0) {
-          float* dst = part_stage + h * (nwarps * NQ * 8);
-          dst[0] = v0;
-          dst[8] = v1;
-          if (VELO) dst[16] = v2;
-        }
-      }
-      __syncwarp();           // every lane has read its counts: the slot may be refilled
-      load_counts(d0 + h);
-    }
-    // Leave the stage.  The LAST warp to get here (a shared-memory counter tells) publishes the stage as completed and
-    // refills the table slot with stage st + NS: the refill is issued the moment the slowest warp leaves the stage,
-    // NS - 1 stages before that warp needs it, and nobody waits for anybody.  The drain of the parked partials is a
-    // rotating duty (see flush_partials) so that it never lands on the slowest warp systematically.
-    {
-      if (lane == 0) {
-        uint32_t old;
-        asm volatile("atom.shared.acq_rel.cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(done0 + 8 * c_slot) : "memory");
-        if (old == (uint32_t)(nwarps - 1)) {
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 8 * c_slot), "r"(0u) : "memory");
-          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(completed_addr), "r"((uint32_t)(st + 1)) : "memory");
-          if (st + NS < n_stages) issue_stage(st + NS, c_slot);
-        }
-      }
-      if (GRAD && st > 0 && drain_next == st - 1) {
-        flush_partials(st - 1);
-        drain_next += nwarps;
-      }
-    }
+    __syncwarp();  // every lane has read its counts: the slot may be refilled
+    load_counts(d0 + h);
+  };
+  // Leave stage st: the tables of the slot and this warp's parked partials are final (the __syncwarp in do_group orders the
+  // other lanes' accesses before lane 0's arrival); then the rotating service duty for the stage that starts next.
+  auto leave_stage = [&](const int st) {
+    if (lane == 0) mbar_arrive(done0 + 8 * c_slot);
     if (++p_slot == NP) p_slot = 0;
     if (++c_slot == NS) {
       c_slot = 0;
       c_phase ^= 1;
     }
+    const int nx = st + 1;
+    if (nx < n_stages && nx >= kSvcDist && ((nx - warp) & (nwarps - 1)) == 0) service(nx - kSvcDist);
+  };
+  int st = 0;
+  while (st < n_stages) {
+    // hot loop: the stages of one batch.  A stage whose batch differs from the current one (a boundary, or -1 = its 16 cells
+    // disagree) leaves it for the slow path below, which comes back with the batch switched or the stage done.
+    for (; st < n_stages; ++st) {
+      mbar_wait(full0 + 8 * c_slot, (uint32_t)c_phase);
+      const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
+      if (__float_as_int(tb_stage[TAIL + 16]) != cur_b) break;
+      const int d0 = (st & 1) * kGPS;
+      const float4* cnt_stage = s_cnt + (size_t)d0 * NLD * nthr;
+      // park address of this lane's cell: [p_slot][warp][quantity][cell][group]
+      float* part_stage = s_part + (((size_t)p_slot * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4))) * 2;
+#pragma unroll
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, h, tb_stage, cnt_stage, part_stage, d0);
+      leave_stage(st);
+    }
+    if (st >= n_stages) break;
+    {
+      const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
+      const int stage_b = __float_as_int(tb_stage[TAIL + 16]);
+      if (stage_b >= 0) {  // batch boundary: switch and re-enter the hot loop at the same stage
+        if (GRAD) flush_batch();
+        cur_b = stage_b;
+        set_batch(cur_b);
+        continue;
+      }
+      const int d0 = (st & 1) * kGPS;
+      const float4* cnt_stage = s_cnt + (size_t)d0 * NLD * nthr;
+      float* part_stage = s_part + (((size_t)p_slot * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4))) * 2;
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, h, tb_stage, cnt_stage, part_stage, d0);
+      leave_stage(st);
+      ++st;
+    }
   }
   cp_async_wait<0>();
-  if (GRAD) {  // the last stage (no successor) and any stage whose drainer finished early
-    for (; drain_next < n_stages; drain_next += nwarps) flush_partials(drain_next);
-  }
+  // the last stages have no successor stage to be serviced from: same rotation, after the loop
+  for (int x = (n_stages >= kSvcDist ? n_stages - kSvcDist : 0); x < n_stages; ++x)
+    if (((x + kSvcDist - warp) & (nwarps - 1)) == 0) service(x);
 
   // ---- flush per-gene partial sums -------------------------------------------------------------------------
-  if (GRAD && P.Nb > 0) flush_batch();
+  if (GRAD) flush_batch();
   constexpr int ROWS = gene_rows(H);
   float* gp = P.genepart + ((long long)split * ROWS) * P.ld;
   auto lane_sum4 = [&](float2 v) -> float2 {  // over the 4 lanes (cells) that share a gene pair
@@ -600,10 +602,19 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       v = lane_sum4(v);
       if (gvalid && q == 0) *reinterpret_cast<float2*>(gp + (long long)row * P.ld + g0) = v;
     };
-    put(ROW_AS, accAS[mt]);
-    put(ROW_LS, accL[mt]);
+    const float4 ga = s_gene[(mt * 2 + 0) * 8];
+    const float2 nr_mt = f2(ga.x, ga.y);
+#ifdef VCB_EXP_OLDACC
+    put(ROW_AS, accKS[mt]);
+    put(ROW_LS, accLS[mt]);
     if (VELO) {
-      put(ROW_AU, accAU[mt]);
+      put(ROW_AU, accKU[mt]);
+#else
+    put(ROW_AS, fma2(nr_mt, accLS[mt], accKS[mt]));                    // sum kS (y - LS) - r sum LS
+    put(ROW_LS, VELO ? add2(accLS[mt], accLU[mt]) : accLS[mt]);
+    if (VELO) {
+      put(ROW_AU, fma2(nr_mt, accLU[mt], accKU[mt]));
+#endif
       if (GRAD) put(ROW_GU, accGU[mt]);
     }
     if (GRAD && gvalid) {
