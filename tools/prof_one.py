@@ -2,6 +2,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from velocycle_b200 import _lib
+if os.environ.get("VCB_LIB"): _lib.LIB_PATH = os.path.abspath(os.environ["VCB_LIB"])
 from velocycle_b200.fused import PackedCounts, fused_elbo_grad
 from velocycle_b200.synthetic import make_synthetic
 Nc = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000

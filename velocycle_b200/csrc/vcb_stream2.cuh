@@ -6,8 +6,11 @@
 //
 //   * a ring stage is TWO 8-cell groups (16 cells): one table copy, one full[] wait, one done[] arrival, one batch
 //     test and one issue test per 16 cells;
-//   * the table ring is refilled by a fixed rotation with a blocking wait on a stage that is already one stage old
-//     (the issuer of stage st retires stage st-1), instead of three non-blocking polls per group in every warp;
+//   * stage service by rotation: warp (x + 2) % 16 services stage x when it enters stage x + 2 -- it waits on the done[]
+//     mbarrier of x (all 16 warps have arrived; normally long ago), re-issues the slot's table copy for stage x + NS and
+//     drains the stage's parked per-cell sums in warp order.  No polling, no completion counter, no warp spins;
+//   * the backward MMAs run as two independent accumulation chains (g terms, w terms): a dependent mma.sync issues ~35
+//     cycles after its predecessor, one six-deep chain per row tile cost 8 % of the kernel;
 //   * nu, the constant term and the size-factor slot are pre-scaled by log2(e) in the A operands, omega by ln 2 in the
 //     table, so the MMA result IS the base-2 exponent; the relu offset 1e-5 rides gamma: m = max(a + eps, eps);
 //   * the backward operands use the 3xTF32 form  G.Z ~ Ghi.Zhi + Ghi.Zlo + Glo.Zhi  with Ghi = G & ~0x1fff and
@@ -32,11 +35,7 @@ constexpr int kD = 4;                            // count groups in flight per w
 constexpr int kMaxNS = 8;                        // table-ring depth limit (mbarrier slots)
 constexpr int kThreads = 512;
 constexpr int kHeader = 256;
-#ifdef VCB_EXP_SVC3
-constexpr int kSvcDist = 3;
-#else
 constexpr int kSvcDist = 2;  // a stage is serviced (table slot refilled, parked cell partials drained) this many stages later
-#endif
 constexpr float kRelEps = 1e-5f;
 
 struct Params {
@@ -226,11 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   // (one row, chunks 0..7) and a consumer quarter-warp (rows 0..3 x two chunks) both touch eight different 16-byte bank
   // groups: neither the copy's shared-memory write nor the consumer's LDS.128 has a bank conflict.  (With the plain
   // consumer-order layout the copy wrote at a 64-byte stride: a 4-way conflict on every LDGSTS.)
-#ifdef VCB_EXP_NOSWZ
-  const uint32_t s_cnt_ld = smem_u32(reinterpret_cast<float4*>(smem_raw + L.cnt_off) + (warp * 32 + 4 * l_chunk + l_row));
-#else
   const uint32_t s_cnt_ld = smem_u32(reinterpret_cast<float4*>(smem_raw + L.cnt_off) + (warp * 32 + l_row * 8 + (l_chunk ^ (2 * l_row))));
-#endif
   const int lgl = warp * 32 + 4 * l_chunk;
   const char* ldS;
   long long u_minus_s = 0;
@@ -308,11 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   for (int s = 0; s < D; ++s) load_counts(s);
 
   const float2 one2 = f2s(1.f), neg1 = f2s(-1.f), eps2 = f2s(kRelEps);
-  #ifdef VCB_EXP_NOSWZ
-  const float4* const s_cnt = reinterpret_cast<const float4*>(smem_raw + L.cnt_off) + tid;
-#else
   const float4* const s_cnt = reinterpret_cast<const float4*>(smem_raw + L.cnt_off) + (warp * 32 + q * 8 + (grp ^ (2 * q)));
-#endif
 
   // One 8-cell group of one batch.  MASKED: compile-time copy used for stages whose cells belong to several batches;
   // cells outside batch `pass_b` are switched off (their counts read as zero, their exponent as -inf).
@@ -388,9 +379,6 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
         const float2 s = add2(u, one2);
         const float2 LS = lg2_2(s);
         accKS[mt] = fma2(kS, fma2(LS, neg1, y), accKS[mt]);
-#ifdef VCB_EXP_OLDACC
-        accKS[mt] = fma2(nr_mt, LS, accKS[mt]);
-#endif
         accLS[mt] = add2(accLS[mt], LS);
         float2 g = zero2, w = zero2;
         if (VELO) {
@@ -402,12 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
           const float2 LU = lg2_2(sU);
           const float2 lmb = lg2_2(mb);
           accKU[mt] = fma2(kU, fma2(LU, neg1, add2(y, lmb)), accKU[mt]);
-#ifdef VCB_EXP_OLDACC
-          accKU[mt] = fma2(nr_mt, LU, accKU[mt]);
-          accLS[mt] = add2(accLS[mt], LU);
-#else
           accLU[mt] = add2(accLU[mt], LU);
-#endif
           if (GRAD) {
             const float2 sUm = mul2(sU, m);
             const float2 rc = rcp_2(mul2(s, sUm));  // one MUFU for 1/s and 1/(sU m)
@@ -545,39 +528,26 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     const int nx = st + 1;
     if (nx < n_stages && nx >= kSvcDist && ((nx - warp) & (nwarps - 1)) == 0) service(nx - kSvcDist);
   };
-  int st = 0;
-  while (st < n_stages) {
-    // hot loop: the stages of one batch.  A stage whose batch differs from the current one (a boundary, or -1 = its 16 cells
-    // disagree) leaves it for the slow path below, which comes back with the batch switched or the stage done.
-    for (; st < n_stages; ++st) {
-      mbar_wait(full0 + 8 * c_slot, (uint32_t)c_phase);
-      const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
-      if (__float_as_int(tb_stage[TAIL + 16]) != cur_b) break;
-      const int d0 = (st & 1) * kGPS;
-      const float4* cnt_stage = s_cnt + (size_t)d0 * NLD * nthr;
-      // park address of this lane's cell: [p_slot][warp][quantity][cell][group]
-      float* part_stage = s_part + (((size_t)p_slot * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4))) * 2;
+  for (int st = 0; st < n_stages; ++st) {
+    mbar_wait(full0 + 8 * c_slot, (uint32_t)c_phase);
+    const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
+    const int d0 = (st & 1) * kGPS;
+    const float4* cnt_stage = s_cnt + (size_t)d0 * NLD * nthr;
+    // park address of this lane's cell: [p_slot][warp][quantity][cell][group]
+    float* part_stage = s_part + (((size_t)p_slot * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4))) * 2;
+    const int stage_b = __float_as_int(tb_stage[TAIL + 16]);  // the stage's batch (0 without batches), -1 if its cells disagree
+    if (stage_b != cur_b && stage_b >= 0) {
+      if (GRAD) flush_batch();
+      cur_b = stage_b;
+      set_batch(cur_b);
+    }
+    if (stage_b >= 0) {
 #pragma unroll
       for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, h, tb_stage, cnt_stage, part_stage, d0);
-      leave_stage(st);
-    }
-    if (st >= n_stages) break;
-    {
-      const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
-      const int stage_b = __float_as_int(tb_stage[TAIL + 16]);
-      if (stage_b >= 0) {  // batch boundary: switch and re-enter the hot loop at the same stage
-        if (GRAD) flush_batch();
-        cur_b = stage_b;
-        set_batch(cur_b);
-        continue;
-      }
-      const int d0 = (st & 1) * kGPS;
-      const float4* cnt_stage = s_cnt + (size_t)d0 * NLD * nthr;
-      float* part_stage = s_part + (((size_t)p_slot * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4))) * 2;
+    } else {
       for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, h, tb_stage, cnt_stage, part_stage, d0);
-      leave_stage(st);
-      ++st;
     }
+    leave_stage(st);
   }
   cp_async_wait<0>();
   // the last stages have no successor stage to be serviced from: same rotation, after the loop
@@ -604,17 +574,10 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     };
     const float4 ga = s_gene[(mt * 2 + 0) * 8];
     const float2 nr_mt = f2(ga.x, ga.y);
-#ifdef VCB_EXP_OLDACC
-    put(ROW_AS, accKS[mt]);
-    put(ROW_LS, accLS[mt]);
-    if (VELO) {
-      put(ROW_AU, accKU[mt]);
-#else
     put(ROW_AS, fma2(nr_mt, accLS[mt], accKS[mt]));                    // sum kS (y - LS) - r sum LS
     put(ROW_LS, VELO ? add2(accLS[mt], accLU[mt]) : accLS[mt]);
     if (VELO) {
       put(ROW_AU, fma2(nr_mt, accLU[mt], accKU[mt]));
-#endif
       if (GRAD) put(ROW_GU, accGU[mt]);
     }
     if (GRAD && gvalid) {
