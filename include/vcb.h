@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define VCB_VERSION 200 /* 0.2.0 */
+#define VCB_VERSION 210 /* 0.2.1 */
 
 #define VCB_MAX_HARMONICS 5 /* gene / angular-speed harmonics compiled in: H in 0..5 */
 
@@ -204,6 +204,53 @@ int vcb_csr_to_counts(const int64_t* indptr, const int32_t* indices, const void*
 int vcb_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                      int64_t* step_dev, float lr0, float lrd, float beta1, float beta2, float eps,
                      float clip, void* stream);
+
+
+/* ---- the non-likelihood part of one Trace_ELBO step, fused (csrc/vcb_svi.cu) ----------------------------------------------
+ * Replaces, for the package's own (model, guide) pairs, what pyro.infer.SVI.step does around the likelihood: the guide's
+ * reparameterised draws (phase_inference_guide.py:47-56, velocity_inference_guide.py:45-63 and :90-141), pack_direction
+ * (utils.py:488-506), the log_prob of every prior and guide site (phase_inference_model.py:361-366,391,
+ * velocity_inference_model.py:323-353,383 and :408-440) and their autograd backward.  Call order of a step:
+ *   vcb_svi_sample -> vcb_phase_fwd_bwd | vcb_velocity_fwd_bwd (on the sampled values) [-> all-reduce] -> vcb_svi_backward
+ *   -> vcb_clipped_adam.
+ * `param` / `grad`: ONE flat fp32 buffer each holding every guide parameter in unconstrained form (positive ones as logs:
+ * transform_to(positive) = exp); the o_* fields are offsets in floats, -1 = the model has no such parameter.  Gradients are
+ * those of loss = -ELBO with respect to the unconstrained values and are OVERWRITTEN.  The eps_* arrays are standard-normal
+ * draws supplied by the caller in the guide's draw order (so a step consumes the RNG stream like the reference does).
+ * model: 0 = phase, 1 = velocity with the mean-field guide, 2 = velocity with the LRMN guide.                               */
+typedef struct vcb_svi_t {
+  int64_t Nc, Ng;
+  int32_t H, Hw, Nb, Nx, rank, model;
+  float* param;
+  float* grad;
+  int64_t o_nu_locs, o_nu_scales;            /* [Ng][K] */
+  int64_t o_dnu_locs;                        /* [Nb][Ng] */
+  int64_t o_phixy_locs;                      /* [Nc][2], even offset */
+  int64_t o_shape_inv_locs;                  /* [Ng] */
+  int64_t o_logbeta_locs, o_logbeta_scales;  /* [Ng] */
+  int64_t o_loggamma_locs, o_loggamma_scales; /* [Ng]            (model 1) */
+  int64_t o_nuw_locs, o_nuw_scales;          /* [Nx][Kw]        (model 1) */
+  int64_t o_loc, o_cov_factor, o_cov_diag;   /* [Ng + Nx Kw], [Ng + Nx Kw][rank], [Ng + Nx Kw]   (model 2) */
+  int64_t o_rho_real_loc;                    /* [Ng]            (model 2) */
+  const float *eps_nu, *eps_loggamma, *eps_logbeta, *eps_nuw, *eps_phixy, *eps_W, *eps_D;
+  const float *mu_nu, *sd_nu;                /* priors, expanded: [Ng][K] */
+  const float *mu_loggamma, *sd_loggamma, *mu_logbeta, *sd_logbeta; /* [Ng] */
+  const float *mu_nuw, *sd_nuw;              /* [Nx][Kw] */
+  const float* phixy_prior;                  /* [Nc][2] */
+  float sd_dnu, gamma_alpha, gamma_beta, rho_mean, rho_std, rho_scale;
+  /* sampled values: written by vcb_svi_sample, inputs of the likelihood call and of vcb_svi_backward */
+  float *nu, *dnu, *shape_inv, *loggamma, *gamma, *logbeta, *nu_omega, *phixy, *phi;
+  /* outputs of the likelihood call (after the all-reduce under cell sharding): inputs of vcb_svi_backward */
+  const float *lp_S, *lp_U, *d_nu, *d_dnu, *d_shape_inv, *d_logbeta, *d_gamma, *d_nu_omega, *d_phi;
+  /* scratch: fp64 block partials, sizes from vcb_svi_partials() */
+  double *cell_partials, *gene_partials, *lik_partials;
+  float* cell_lp; /* sum over this rank's cells of log p(phixy) - log q(phixy); lives in the all-reduced buffer under sharding */
+  float* loss;    /* the step's ELBO loss, written by vcb_svi_backward */
+} vcb_svi_t;
+
+int vcb_svi_partials(int64_t Nc, int64_t Ng, int64_t* n_cell_blocks, int64_t* n_gene_blocks);
+int vcb_svi_sample(const vcb_svi_t* p, void* stream);
+int vcb_svi_backward(const vcb_svi_t* p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,26 @@ class VcbProblem(C.Structure):
     ]
 
 
+class VcbSvi(C.Structure):
+    """``vcb_svi_t`` of include/vcb.h (field for field)."""
+
+    _fields_ = (
+        [("Nc", C.c_int64), ("Ng", C.c_int64)]
+        + [(n, C.c_int32) for n in ("H", "Hw", "Nb", "Nx", "rank", "model")]
+        + [("param", C.c_void_p), ("grad", C.c_void_p)]
+        + [(n, C.c_int64) for n in ("o_nu_locs", "o_nu_scales", "o_dnu_locs", "o_phixy_locs", "o_shape_inv_locs",
+                                    "o_logbeta_locs", "o_logbeta_scales", "o_loggamma_locs", "o_loggamma_scales",
+                                    "o_nuw_locs", "o_nuw_scales", "o_loc", "o_cov_factor", "o_cov_diag", "o_rho_real_loc")]
+        + [(n, C.c_void_p) for n in ("eps_nu", "eps_loggamma", "eps_logbeta", "eps_nuw", "eps_phixy", "eps_W", "eps_D",
+                                     "mu_nu", "sd_nu", "mu_loggamma", "sd_loggamma", "mu_logbeta", "sd_logbeta",
+                                     "mu_nuw", "sd_nuw", "phixy_prior")]
+        + [(n, C.c_float) for n in ("sd_dnu", "gamma_alpha", "gamma_beta", "rho_mean", "rho_std", "rho_scale")]
+        + [(n, C.c_void_p) for n in ("nu", "dnu", "shape_inv", "loggamma", "gamma", "logbeta", "nu_omega", "phixy", "phi",
+                                     "lp_S", "lp_U", "d_nu", "d_dnu", "d_shape_inv", "d_logbeta", "d_gamma", "d_nu_omega",
+                                     "d_phi", "cell_partials", "gene_partials", "lik_partials", "cell_lp", "loss")]
+    )
+
+
 EXPORTS = (
     "vcb_version",
     "vcb_strerror",
@@ -60,6 +80,9 @@ EXPORTS = (
     "vcb_expand_counts_packed",
     "vcb_expand_counts_twolevel",
     "vcb_clipped_adam",
+    "vcb_svi_partials",
+    "vcb_svi_sample",
+    "vcb_svi_backward",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -112,6 +135,12 @@ def load() -> C.CDLL:
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
         C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p,
     ]
+    lib.vcb_svi_partials.restype = C.c_int
+    lib.vcb_svi_partials.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    for name in ("vcb_svi_sample", "vcb_svi_backward"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(VcbSvi), C.c_void_p]
     _lib = lib
     return lib
 

@@ -7,9 +7,10 @@ dozen host syncs per step: guide sampling, prior log-probs, ``.item()`` per site
 than the fused likelihood kernel.  ``GraphedSVI`` keeps the model / guide functions and their semantics but
 
 * moves every (unconstrained) parameter into ONE flat fp32 buffer (gradients, Adam moments likewise),
-* traces guide and model once through the effect handlers while a CUDA graph is being captured -- so the graph
-  holds exactly the kernels of one Trace_ELBO step: guide draws (graph-safe Philox RNG), the fused C-ABI launch
-  sequence, the NCCL all-reduce under cell sharding, the backward, and
+* runs the step as a dozen launches when model and guide are the package's own (``faststep.FusedStep``: torch draws in
+  the guide's order, ``vcb_svi_sample``, the likelihood, the all-reduce under cell sharding, ``vcb_svi_backward``);
+  any other (conditioned, user-written) pair is traced once through the effect handlers while a CUDA graph is being
+  captured -- the graph then holds exactly the kernels of one Trace_ELBO step -- and
 * ends with the fused multi-tensor ``vcb_clipped_adam`` kernel (device-side step counter, so replays advance it).
 
 ``step()`` replays the graph and reads back the loss (one 4-byte D2H copy).  Distribution argument validation is
@@ -31,8 +32,13 @@ __all__ = ["GraphedSVI"]
 
 class GraphedSVI:
     def __init__(self, model: Callable, guide: Callable, optim_args: Dict, mp, use_graph: bool = True,
-                 warmup_iters: int = 3):
+                 warmup_iters: int = 3, fast: bool = True):
+        """``fast``: use the fused step (``faststep.FusedStep``: a dozen launches) when ``model`` / ``guide`` are the package's
+        own unconditioned functions; otherwise -- and always with ``fast=False`` -- the step is traced through the effect
+        handlers like ``pyro.infer.SVI`` does."""
         self.model, self.guide, self.mp = model, guide, mp
+        self._want_fast = fast
+        self._fast = None
         self.lr0 = float(optim_args.get("lr", 1e-3))
         self.lrd = float(optim_args.get("lrd", 1.0))
         self.betas = tuple(optim_args.get("betas", (0.9, 0.999)))
@@ -60,9 +66,10 @@ class GraphedSVI:
         store = pyro.get_param_store()
         names = list(store.keys())
         sizes = [store.get_unconstrained(n).numel() for n in names]
-        total = sum(sizes)
+        pad = lambda n: (n + 3) // 4 * 4  # every tensor starts on a 16-byte boundary (vector access in the fused kernels)
+        total = sum(pad(sz) for sz in sizes)
         dev = self.device
-        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -78,10 +85,23 @@ class GraphedSVI:
             view.grad = self.flat_grad[off: off + sz].view(old.shape)
             store.set_unconstrained(n, view, store.get_constraint(n))
             self.param_slices[n] = (off, sz)
-            off += sz
+            off += pad(sz)
+
+    def _adam(self) -> None:
+        rc = self._lib.vcb_clipped_adam(
+            self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+            self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.step_dev.data_ptr(),
+            self.lr0, self.lrd, self.betas[0], self.betas[1], self.eps, self.clip,
+            torch.cuda.current_stream(self.device).cuda_stream,
+        )
+        _lib.check(rc, "vcb_clipped_adam")
 
     def _body(self) -> None:
         """One Trace_ELBO(num_particles=1) step with every value kept on the device."""
+        if self._fast is not None:
+            self._fast.body()  # draws, vcb_svi_sample, likelihood, [all-reduce], vcb_svi_backward: loss_buf and flat_grad
+            self._adam()
+            return
         _, _, poutine, _, _ = backend.get()
         self.flat_grad.zero_()
         guide_trace = poutine.trace(self.guide).get_trace(self.mp)
@@ -98,13 +118,7 @@ class GraphedSVI:
         loss = -surrogate
         loss.backward()
         self.loss_buf.copy_(loss.detach())
-        rc = self._lib.vcb_clipped_adam(
-            self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
-            self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.step_dev.data_ptr(),
-            self.lr0, self.lrd, self.betas[0], self.betas[1], self.eps, self.clip,
-            torch.cuda.current_stream(self.device).cuda_stream,
-        )
-        _lib.check(rc, "vcb_clipped_adam")
+        self._adam()
 
     def _build(self) -> None:
         from .ppl import primitives
@@ -115,6 +129,12 @@ class GraphedSVI:
         self._flatten_params()
         torch.cuda.set_rng_state(rng_cuda, self.device)
         torch.set_rng_state(rng_cpu)
+        if self._want_fast:
+            from .faststep import FusedStep, model_code
+
+            code = model_code(self.model, self.guide, self.mp)
+            if code is not None:
+                self._fast = FusedStep(self, code)
         self._validation_prev = primitives.validation_enabled()
         if not self._use_graph:
             self._built = True
