@@ -237,6 +237,8 @@ typedef struct vcb_svi_t {
   const float *mu_loggamma, *sd_loggamma, *mu_logbeta, *sd_logbeta; /* [Ng] */
   const float *mu_nuw, *sd_nuw;              /* [Nx][Kw] */
   const float* phixy_prior;                  /* [Nc][2] */
+  const int64_t* cell_row;                   /* [Nc] or NULL: row of cell c in the (batch-sorted) count matrices; phi and d_phi
+                                                are indexed by row, everything else here by cell */
   float sd_dnu, gamma_alpha, gamma_beta, rho_mean, rho_std, rho_scale;
   /* sampled values: written by vcb_svi_sample, inputs of the likelihood call and of vcb_svi_backward */
   float *nu, *dnu, *shape_inv, *loggamma, *gamma, *logbeta, *nu_omega, *phixy, *phi;

@@ -9,7 +9,7 @@ import math
 import pytest
 import torch
 
-from oracle.likelihood import analytic_gradients, fused_reference
+from oracle.likelihood import analytic_gradients, fused_reference, fused_reference_chunked
 
 pytestmark = pytest.mark.gpu
 
@@ -67,9 +67,10 @@ def _run(d, velocity, with_dnu=True, inline=False, grad=True, perturb=0.3, seed=
 def _compare(out, ref, tol=TOL, ref32=None):
     ref = dict(ref)
     ref32 = ref.pop("_ref32", ref32)
-    """Normwise error against the fp64 oracle: <= 1e-4, or -- where fp32 evaluation of the reference op
-    chain itself is further than that from fp64 (cancellation in d/dshape_inv at small Nc, relu sign flips)
-    -- at least as close to the truth as the reference's own fp32 arithmetic (factor 2 slack)."""
+    """Normwise error against the fp64 oracle: <= 1e-4 for every tensor.  One exception: d/dshape_inv =
+    -r^2 (psi - L - dnu0 / r) is a difference of sums ~1e3 times larger than itself, so at a few hundred cells fp32
+    evaluation of the reference op chain itself is further than 1e-4 from fp64; there the bound is twice the
+    reference's own fp32 error."""
     checked = 0
     for k, v in ref.items():
         if k in ("total", "omega") or k not in out:
@@ -78,7 +79,7 @@ def _compare(out, ref, tol=TOL, ref32=None):
         assert torch.isfinite(got).all(), k
         err = float((got - v).abs().max() / (v.abs().max() + 1e-30))
         bound = tol
-        if ref32 is not None and k in ref32:
+        if k == "d_shape_inv" and ref32 is not None and k in ref32:  # the one documented exception (cancellation)
             e32 = float((ref32[k].double().reshape(v.shape) - v).abs().max() / (v.abs().max() + 1e-30))
             bound = max(tol, 2.0 * e32)
         assert err <= bound, f"{k}: normwise rel err {err:.3e} > {bound:.3e}"
@@ -152,39 +153,66 @@ def test_results_are_deterministic(monkeypatch):
             assert torch.equal(a[k], b[k]), k
 
 
-def test_full_size_properties():
-    """BASELINE's 1M x 2k is far beyond what the CPU oracle evaluates in seconds; check size-independent properties:
-    (i) additivity over cells: per-gene sums of the whole matrix = sum over two row blocks evaluated separately
-    (every per-gene output is a plain sum over cells), (ii) per-cell outputs do not depend on the other cells."""
+def _perturbed(Nc, Ng, Nb, Nx, seed, sorted_batches=True):
+    """Synthetic data evaluated away from the generating parameters, gamma lifted off the relu kink (see _run)."""
+    from velocycle_b200.synthetic import fourier_rows, make_synthetic
+
+    d = make_synthetic(Nc, Ng, H=3, Hw=1, Nb=Nb, Nx=Nx, seed=seed, device="cuda", stats=False, sorted_batches=sorted_batches)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    jit = lambda t, s=0.3: t + s * torch.randn(t.shape, generator=g).to(t.device)
+    d.nu, d.phi, d.logbeta, d.loggamma = jit(d.nu), jit(d.phi), jit(d.logbeta), jit(d.loggamma)
+    d.shape_inv = d.shape_inv * torch.exp(jit(torch.zeros_like(d.shape_inv)))
+    d.nu_omega = jit(d.nu_omega, 0.1)
+    dd = fourier_rows(d.phi, 3, 1) @ d.nu.T
+    om = (fourier_rows(d.phi, 1, 0) * d.nu_omega[d.cond_id.long()]).sum(-1)
+    d.loggamma = torch.maximum(d.loggamma, torch.log((-(dd * om[:, None])).amax(0).clamp_min(0.0) + 0.05))
+    return d
+
+
+def _against_chunked_oracle(d, with_dnu):
     from velocycle_b200.fused import PackedCounts, fused_elbo_grad
-    from velocycle_b200.synthetic import make_synthetic
 
-    Nc, cut = 200_000, 77_777  # (kept below 1M so that the test box needs ~5 GB; the code path is size-agnostic)
-    d = make_synthetic(Nc, 2000, H=3, Hw=1, Nb=1, Nx=1, seed=17, device="cuda", stats=False)
-    d.shape_inv = d.shape_inv * 2.0  # away from the optimum: d/dshape_inv is then not pure cancellation noise
-    d.nu = d.nu + 0.2 * torch.randn(d.nu.shape, generator=torch.Generator().manual_seed(1)).to(d.nu.device)
-    gamma = torch.exp(d.loggamma)
+    counts = PackedCounts(d.S, d.U, d.Ng, d.batch_id, d.cond_id)
+    p = _problem(d, True, with_dnu)
+    out = fused_elbo_grad(counts, p["phi"], p["cf"], p["nu"], p.get("dnu"), p["shape_inv"], p["logbeta"], p["gamma"],
+                          p["nu_omega"], grad=True, want_d_omega=True)
+    torch.cuda.synchronize()
+    ref = fused_reference_chunked(p, dtype=torch.float64)
+    for k, v in ref.items():
+        if k in ("total", "omega") or k not in out:
+            continue
+        got = out[k].double().cpu().reshape(v.shape)
+        err = float((got - v).abs().max() / (v.abs().max() + 1e-30))
+        # d/dshape_inv = -r^2 (psi - L - dnu0/r) is a difference of sums ~1e3 times larger than itself: fp32 partial sums
+        # over 1e5 cells leave it ~1e-3 accurate in ANY fp32 evaluation (the small-shape tests bound it by the reference's
+        # own fp32 error); every other tensor: the 1e-4 contract
+        assert err <= (2e-3 if k == "d_shape_inv" else TOL), f"{k}: normwise rel err {err:.3e}"
+    tot = out["lp_S"].double().sum().item() + out["lp_U"].double().sum().item()
+    assert abs(tot - float(ref["total"])) <= TOL * abs(float(ref["total"]))
+    return counts
 
-    def run(lo, hi):
-        c = PackedCounts(d.S[lo:hi], d.U[lo:hi], d.Ng, d.batch_id[lo:hi], d.cond_id[lo:hi])
-        return fused_elbo_grad(c, d.phi[lo:hi], d.cf[lo:hi], d.nu, None, d.shape_inv, d.logbeta, gamma, d.nu_omega,
-                               grad=True)
 
-    whole, a, b = run(0, Nc), run(0, cut), run(cut, Nc)
-    for k in ("d_nu", "d_logbeta", "d_gamma", "d_nu_omega"):
-        want = a[k].double() + b[k].double()
-        err = float((whole[k].double() - want).abs().max() / want.abs().max())
-        assert err <= 1e-5, (k, err)
-    # these also carry the count-spectrum terms, additive over cells as well; d/dshape_inv is a difference of
-    # sums ~1e3 times larger than itself (psi - L - dnu0/r), so fp32 partial sums leave it ~1e-3 accurate
-    for k, tol in (("lp_S", 1e-5), ("lp_U", 1e-5), ("d_shape_inv", 2e-3)):
-        want = a[k].double() + b[k].double()
-        err = float((whole[k].double() - want).abs().max() / want.abs().max())
-        assert err <= tol, (k, err)
-    for k in ("d_phi", "d_cf"):
-        want = torch.cat([a[k], b[k]]).double()
-        err = float((whole[k].double() - want).abs().max() / want.abs().max())
-        assert err <= 1e-5, (k, err)
+def test_config_c3_100k_x_2k_matches_oracle():
+    """BASELINE config C3 (100 000 cells x 2 000 genes, H = 3, velocity): the kernel against the fp64 op chain evaluated in
+    cell blocks -- 4 gene tiles x 37 cell splits, ~170 ring stages per CTA."""
+    _against_chunked_oracle(_perturbed(100_000, 2000, 1, 1, seed=17), with_dnu=False)
+
+
+def test_config_c5_tiling_16_batches_matches_oracle():
+    """BASELINE config C5's tiling (5 000 genes = 10 gene tiles, 16 batches with per-batch gene offsets, 2 conditions) on
+    20 000 cells handed over in SHUFFLED batch order: PackedCounts sorts the rows by batch once, the kernel switches offsets
+    at stage boundaries inside CTAs, results come back in the caller's cell order -- and twice the same bits."""
+    from velocycle_b200.fused import fused_elbo_grad
+
+    d = _perturbed(20_000, 5000, 16, 2, seed=23, sorted_batches=False)
+    counts = _against_chunked_oracle(d, with_dnu=True)
+    assert counts.perm is not None
+    p = _problem(d, True, True)
+    args = (counts, p["phi"], p["cf"], p["nu"], p["dnu"], p["shape_inv"], p["logbeta"], p["gamma"], p["nu_omega"])
+    a = {k: v.clone() for k, v in fused_elbo_grad(*args, grad=True).items() if not k.startswith("_")}
+    b = fused_elbo_grad(*args, grad=True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
 
 
 @pytest.mark.parametrize("velocity", [False, True])
@@ -261,6 +289,33 @@ def test_matches_fp32_reference_chain():
         # the fused path must be at least as close to the fp64 truth as 1e-4, and the fp32 chain within the same band
         assert e_ours <= TOL, (k, e_ours)
         assert e_ref32 <= 10 * TOL, (k, e_ref32)
+
+
+def test_at_the_relu_kink_no_worse_than_the_fp32_reference_chain():
+    """Elements with a = d*omega + gamma in (0, 0.05): dL/da = kU / m reaches 1e5 kU at m = relu(a) + 1e-5, so fp32
+    rounding of `a` alone moves the gamma / nu / phi / nu_omega gradients by up to per cent in ANY fp32 evaluation.  Here
+    gamma is set so that thousands of elements sit in that band (none lifted away), and the kernel must be as close to
+    the fp64 truth as the reference's own fp32 op chain is (factor 3: both errors are a few sign-flip sized rounding
+    events, i.e. noisy), tensor by tensor; tensors the kink does not touch keep the 1e-4 contract."""
+    from velocycle_b200.synthetic import fourier_rows, make_synthetic
+
+    d = make_synthetic(512, 128, H=2, Hw=1, Nb=1, Nx=1, seed=31, device="cuda")
+    dd = fourier_rows(d.phi, 2, 1) @ d.nu.T
+    om = (fourier_rows(d.phi, 1, 0) * d.nu_omega[d.cond_id.long()]).sum(-1)
+    a_wo_gamma = dd * om[:, None]
+    # per gene: gamma = a quantile of -d*omega, so that a = d*omega + gamma straddles zero for that gene
+    d.loggamma = torch.log((-a_wo_gamma).quantile(0.7, dim=0).clamp_min(1e-3))
+    a = a_wo_gamma + torch.exp(d.loggamma)[None, :]
+    n_band = int(((a > 0) & (a < 0.05)).sum())
+    assert n_band > 500, n_band
+    out, ref64, p = _run(d, True, perturb=0.0, relu_margin=None)
+    ref32 = ref64.pop("_ref32")
+    for k in ("d_nu", "d_phi", "d_gamma", "d_nu_omega", "d_omega", "d_logbeta", "d_shape_inv", "lp_S", "lp_U"):
+        v = ref64[k]
+        got = out[k].double().cpu().reshape(v.shape)
+        e_ours = float((got - v).abs().max() / v.abs().max())
+        e_ref32 = float((ref32[k].double().reshape(v.shape) - v).abs().max() / v.abs().max())
+        assert e_ours <= max(TOL, 3.0 * e_ref32), (k, e_ours, e_ref32)
 
 
 def test_autograd_function_scales_and_poisons():

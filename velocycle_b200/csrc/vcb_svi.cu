@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kSviThreads) vcb_svi_cell_sample_kernel(const 
     const float2 pr = reinterpret_cast<const float2*>(P.phixy_prior)[c];
     const float x = loc.x + e.x, y = loc.y + e.y;  // Normal(locs, 1).rsample()
     reinterpret_cast<float2*>(P.phixy)[c] = make_float2(x, y);
-    P.phi[c] = atan2f(y, x);  // pack_direction, utils.py:488-506
+    P.phi[P.cell_row ? P.cell_row[c] : c] = atan2f(y, x);  // pack_direction, utils.py:488-506
     const double dx = (double)x - pr.x, dy = (double)y - pr.y;
     // log p - log q: Normal(prior, 1) against Normal(locs, 1) at locs + eps; the 2 x 1/2 log 2pi cancel
     lp = -0.5 * (dx * dx + dy * dy) + 0.5 * ((double)e.x * e.x + (double)e.y * e.y);
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kSviThreads) vcb_svi_cell_backward_kernel(cons
   if (c >= P.Nc) return;
   const float2 z = reinterpret_cast<const float2*>(P.phixy)[c];
   const float2 pr = reinterpret_cast<const float2*>(P.phixy_prior)[c];
-  const float dphi = P.d_phi[c];
+  const float dphi = P.d_phi[P.cell_row ? P.cell_row[c] : c];
   const float r2 = z.x * z.x + z.y * z.y;
   // phi = atan2(y, x): dphi/dx = -y / r2, dphi/dy = x / r2; the guide's log q does not depend on locs (pathwise)
   const float ex = dphi * (-z.y / r2) - (z.x - pr.x);

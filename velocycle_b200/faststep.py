@@ -143,6 +143,9 @@ class FusedStep:
         q.flags = VCB_FLAG_GRAD
         q.S = counts.S.data_ptr()
         cf = self.mp.count_factor.detach().reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+        if counts.perm is not None:  # rows sorted by batch (PackedCounts): phi / d_phi live in row order, cf is permuted once
+            cf = cf[counts.perm].contiguous()
+            self.p.cell_row = counts.inv_perm.data_ptr()
         self._keep.append(cf)
         q.phi, q.cf = self.phi.data_ptr(), cf.data_ptr()
         if Nb > 0 and counts.batch_id is None:

@@ -405,6 +405,22 @@ class PackedCounts:
         dev = S.device
         self.batch_id = None if batch_id is None else batch_id.to(device=dev, dtype=torch.int32).contiguous()
         self.cond_id = None if cond_id is None else cond_id.to(device=dev, dtype=torch.int32).contiguous()
+        # The streaming kernel switches the batch offsets per 16-cell stage; a stage that mixes batches takes a masked pass
+        # per batch present.  Design matrices come in arbitrary cell order (preprocessing.py:65-93), so cells are stably
+        # sorted by batch ONCE here: rows of S / U and the ids are reordered (a copy, only when the input is not sorted
+        # already), `perm[i]` = caller's index of the cell in row i.  Per-cell inputs / outputs of a call are permuted at the
+        # wrapper (fused_elbo_grad) or inside the fused step's cell kernels; after sorting at most Nb - 1 stages are mixed.
+        self.perm = self.inv_perm = None
+        if self.batch_id is not None and self.Nc > 1 and bool((self.batch_id[1:] < self.batch_id[:-1]).any()):
+            self.perm = torch.argsort(self.batch_id.long(), stable=True)
+            self.inv_perm = torch.empty_like(self.perm)
+            self.inv_perm[self.perm] = torch.arange(self.Nc, device=dev)
+            self.S = self.S.index_select(0, self.perm)
+            if self.U is not None:
+                self.U = self.U.index_select(0, self.perm)
+            self.batch_id = self.batch_id[self.perm].contiguous()
+            if self.cond_id is not None:
+                self.cond_id = self.cond_id[self.perm].contiguous()
         self.spec_S = self.spec_U = None
         if spectrum:
             self.build_spectra()
@@ -508,10 +524,14 @@ def fused_elbo_grad(
     velocity = nu_omega is not None
     Nc, Ng, ld = counts.Nc, counts.Ng, counts.ld
     phi = _dev_f32(phi, "phi").reshape(-1)
+    if counts.perm is not None:  # rows are sorted by batch: per-cell inputs follow
+        phi = phi[counts.perm]
     nu = _dev_f32(nu, "nu").reshape(Ng, -1)
     K = nu.shape[1]
     shape_inv = _dev_f32(shape_inv, "shape_inv").reshape(-1)
     cf = None if cf is None else _dev_f32(cf, "cf").reshape(-1)
+    if cf is not None and counts.perm is not None:
+        cf = cf[counts.perm]
     assert phi.numel() == Nc and shape_inv.numel() == Ng and K % 2 == 1
     Nb = 0
     if dnu is not None:
@@ -590,6 +610,10 @@ def fused_elbo_grad(
     _lib.check(fn(C.byref(p), ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream),
                "vcb_velocity_fwd_bwd" if velocity else "vcb_phase_fwd_bwd")
     out["_workspace"] = ws  # keep alive until the stream has consumed it
+    if counts.perm is not None:  # per-cell outputs back in the caller's cell order
+        for k in ("d_phi", "d_cf", "d_omega"):
+            if k in out:
+                out[k] = out[k][counts.inv_perm]
     return out
 
 
