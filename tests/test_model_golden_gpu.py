@@ -102,6 +102,10 @@ def test_conditioned_velocity_fit_driver_runs_and_matches():
     fit.fit(ClippedAdam({"lr": 0.03, "betas": (0.8, 0.99)}), num_steps=15, verbose=False)
     assert len(fit.losses) == 15 and np.isfinite(fit.losses).all()
     assert fit.losses[-1] < fit.losses[0]
+    # the driver ran the captured-graph step (traced once: the conditioned sites are constants inside the graph), not the
+    # fused step, which only serves the unconditioned pairs
+    g = next(iter(fit._steppers.values()))[0]
+    assert g._graph is not None and g._fast is None and g.steps_done == 15
     assert fit.posterior["νω"].shape[0] == 4 and fit.posterior["ω"].shape[-1] == mp.Nc
     # conditioned sites receive no updates
     assert torch.equal(pyro.param("ϕxy_locs").detach().cpu(), inp["phixy_prior"].float())
@@ -133,6 +137,8 @@ def test_phase_fit_driver_returns_containers():
     fit = PhaseFitModel(mp, num_samples=2, n_per_bin=2)
     fit.fit(ClippedAdam({"lr": 0.03, "betas": (0.8, 0.99)}), num_steps=8, verbose=False)
     assert len(fit.losses) == 8 and np.isfinite(fit.losses).all()
+    g = next(iter(fit._steppers.values()))[0]
+    assert g._graph is not None and g._fast is not None  # the reference's public entry point runs the fused, graphed step
     K = mp.μνg.shape[-1]
     assert fit.cycle_pyro.means.shape == (K, mp.Ng) and np.array_equal(fit.cycle_pyro.stds.values, fit.fourier_coef_sd)
     assert fit.cycle_pyro.disp_pyro.shape == (mp.Ng,)

@@ -95,12 +95,13 @@ class PhaseFitModel:
     def fit(self, optimizer, loss=None, num_steps=1000, intermediate_output_step_size=100, store_output=False,
             verbose=True):
         pyro, _, _, infer, _ = backend.get()
-        loss = infer.Trace_ELBO(num_particles=1) if loss is None else loss
-        svi = infer.SVI(self.model, self.guide, optimizer, loss)
+        from .svi import agree_across_ranks, stepper_for
+
+        svi_step = stepper_for(self, self.model, self.guide, optimizer, loss, self.metaparams)
         losses, intermediate_output = [], []
         early_exit_bool = False
         for step in range(num_steps):
-            step_loss = svi.step(self.metaparams)
+            step_loss = svi_step()
             losses.append(step_loss)
             if store_output and step % intermediate_output_step_size == 0:
                 intermediate_output.append(self.sample_posterior(num_samples=50))
@@ -108,7 +109,7 @@ class PhaseFitModel:
             if verbose and step > 5 and step % 40 == 0:
                 logging.info("step %d ELBO loss %.6g", step, step_loss)
             if early_exit_bool:
-                if np.abs(np.mean(losses[-100:]) - np.mean(losses[-10:])) < 5:
+                if agree_across_ranks(bool(np.abs(np.mean(losses[-100:]) - np.mean(losses[-10:])) < 5), self.metaparams):
                     break
             elif step > 200 and self.early_exit:
                 early_exit_bool = True

@@ -27,7 +27,54 @@ import torch
 from . import _lib
 from .ppl import backend
 
-__all__ = ["GraphedSVI"]
+__all__ = ["GraphedSVI", "stepper_for", "agree_across_ranks"]
+
+
+def stepper_for(owner, model: Callable, guide: Callable, optimizer, loss, mp):
+    """The step function the fit drivers loop over (``PhaseFitModel.fit`` / ``VelocityFitModel.fit``,
+    ``phase_inference_model.py:162-169``, ``velocity_inference_model.py:111-120``): ``GraphedSVI.step`` when the data live on
+    a CUDA device, the optimizer is this package's ``ClippedAdam`` and the loss the default single-particle ``Trace_ELBO``
+    -- the fused step for the package's own model / guide, a captured trace for conditioned ones; anything else (custom
+    losses or optimizers, real Pyro as the backend) gets the eager ``SVI.step``.  The stepper is cached on ``owner`` per
+    optimizer object, so a second ``fit`` with the same optimizer continues its Adam state and learning-rate decay like
+    Pyro's per-parameter optimizers do."""
+    from .ppl import infer as shim_infer, optim as shim_optim
+
+    pyro, _, _, infer, _ = backend.get()
+    dev = torch.device(mp.device)
+    args = getattr(optimizer, "pt_optim_args", None)
+    graphable = (
+        dev.type == "cuda" and infer is shim_infer and isinstance(optimizer, shim_optim.PyroOptim)
+        and optimizer.pt_optim_constructor is shim_optim.TorchClippedAdam and isinstance(args, dict)
+        and (loss is None or (isinstance(loss, shim_infer.Trace_ELBO) and loss.num_particles == 1))
+        and float(args.get("weight_decay", 0.0)) == 0.0
+    )
+    if not graphable:
+        loss = infer.Trace_ELBO(num_particles=1) if loss is None else loss
+        svi = infer.SVI(model, guide, optimizer, loss)
+        return lambda: svi.step(mp)
+    cache = getattr(owner, "_steppers", None)
+    if cache is None:
+        cache = owner._steppers = {}
+    key = (id(optimizer), id(model), id(guide))
+    if key not in cache:
+        cache.clear()  # one live graph per driver: the flat buffers of an older one are re-homed by the new one
+        cache[key] = (GraphedSVI(model, guide, dict(args), mp), optimizer)  # (the optimizer is kept alive: its id is the key)
+    g = cache[key][0]
+    return g.step
+
+
+def agree_across_ranks(flag: bool, mp) -> bool:
+    """Under cell sharding every rank must take the same early-exit decision (a rank that leaves the loop alone hangs the
+    others in the step's all-reduce): rank 0's decides."""
+    import torch.distributed as dist
+
+    shard = getattr(mp, "shard", None)
+    if shard is None or shard.world <= 1 or not dist.is_initialized():
+        return flag
+    t = torch.tensor([1 if flag else 0], device=torch.device(mp.device) if torch.device(mp.device).type == "cuda" else "cpu")
+    dist.broadcast(t, src=dist.get_global_rank(shard.group, 0) if shard.group is not None else 0, group=shard.group)
+    return bool(int(t.item()))
 
 
 class GraphedSVI:
@@ -117,6 +164,21 @@ class GraphedSVI:
                 surrogate = surrogate - site["log_prob_sum"]
         loss = -surrogate
         loss.backward()
+        shard = getattr(self.mp, "shard", None)
+        if shard is not None and shard.world > 1:
+            # the likelihood sites are global already (all-reduced inside the fused op) and the gene-level terms replicated;
+            # the per-cell site is the rank's own: report the global ELBO, identical on every rank
+            import torch.distributed as dist
+
+            local = 0.0
+            for tr, sign in ((model_trace, 1.0), (guide_trace, -1.0)):
+                site = tr.nodes.get("ϕxy")
+                if site is not None and site["type"] == "sample":
+                    local = local + sign * site["log_prob_sum"].detach()
+            if isinstance(local, torch.Tensor):
+                total = local.clone()
+                dist.all_reduce(total, group=shard.group)
+                loss = loss.detach() + local - total
         self.loss_buf.copy_(loss.detach())
         self._adam()
 

@@ -125,12 +125,13 @@ class VelocityFitModel:
             print("USER WARNING: the number of genes is below the recommended number for reliable velocity-learning.")
         if (mp.Ng < 350) & (mp.Nc < 50):
             print("USER WARNING: the number of cells is below the recommended number for reliable velocity-learning.")
-        loss = infer.Trace_ELBO(num_particles=1) if loss is None else loss
-        svi = infer.SVI(self.model, self.guide, optimizer, loss)
+        from .svi import agree_across_ranks, stepper_for
+
+        svi_step = stepper_for(self, self.model, self.guide, optimizer, loss, mp)
         losses, intermediate_output = [], []
         early_exit_bool = False
         for step in range(num_steps):
-            step_loss = svi.step(mp)
+            step_loss = svi_step()
             losses.append(step_loss)
             if store_output and step % intermediate_output_step_size == 0:
                 logging.info("Elbo loss: {}".format(step_loss))
@@ -138,7 +139,7 @@ class VelocityFitModel:
             if verbose and step > 5 and step % 40 == 0:
                 logging.info("step %d ELBO loss %.6g", step, step_loss)
             if early_exit_bool:
-                if np.abs(np.mean(losses[-100:]) - np.mean(losses[-10:])) < 5:
+                if agree_across_ranks(bool(np.abs(np.mean(losses[-100:]) - np.mean(losses[-10:])) < 5), self.metaparams):
                     break
             elif step > 200 and self.early_exit:
                 early_exit_bool = True
