@@ -1,24 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- the headline benchmark of the hot path (contract: see the task statement / DESIGN.md section 6).
+"""bench.py -- the headline benchmark of the hot path (contract: the task statement / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one full SVI step of the velocity model (guide draw -> fused ELBO + every gradient over the
-spliced and unspliced count matrices -> gene-gradient all-reduce when N > 1 -> ClippedAdam) through the public
-API ``GraphedSVI(model, guide, optim_args, mp).step()`` (the drop-in model/guide functions traced once into a
-CUDA graph; ``--eager`` times ``ppl.infer.SVI.step`` instead) on synthetic counts, loss read back every step.  Workload per GPU (weak scaling):
-1,000,000 cells x 2,000 genes, 3 gene harmonics, 1 angular-speed harmonic -- the single-GPU target shape of
-BASELINE.json's north_star; 16 GB of fp32 counts per GPU, far beyond the 126 MB L2, so no flush is needed.
+A "step" is one full SVI step of the velocity model (guide draws -> fused ELBO + every gradient over the spliced and
+unspliced count matrices -> gene-gradient all-reduce when N > 1 -> ClippedAdam) through the step function the reference's
+public entry point loops over: ``VelocityFitModel.fit`` obtains it from ``svi.stepper_for`` (a ``GraphedSVI.step``: the
+whole step replayed as one CUDA graph, loss read back every step like ``pyro.infer.SVI.step``).
 
-``value``  : cell.gene negative-binomial evaluations per second (cells x genes x steps/s; each counts S and U),
-             counts resident in HBM (as the reference keeps them: preprocessing.py:193-194).
-``e2e``    : the same step when the count shard starts each step in pinned HOST memory and is copied to the
-             device inside the timed region, plus the device->host read of the loss.
-``roofline``: the streaming kernel's algorithmic bytes (8 B per cell.gene: one fp32 S and U each) over its
-             CUDA-event duration, against the measured HBM peak of MEASURED_PEAKS.json.
-``cpu_baseline``: the reference op chain (oracle/models.py: unfused (Ng,Nc) einsum + GammaPoisson + autograd
-             under the same SVI) on the host cores, on a bounded sample of the same workload.
+Workloads (BASELINE.json):
+  N = 1 : 1,000,000 cells x 2,000 genes, H = 3, Hw = 1 -- the single-GPU target shape of north_star (16 GB of fp32 counts,
+          far beyond the 126 MB L2: no flush needed).
+  N > 1 : config C4, 2,000,000 cells x 2,000 genes in total, cell-sharded (2M / N cells per GPU): STRONG scaling; the weak
+          figure (1M cells per GPU) rides along as ``weak``.  Before timing, 6 steps of the golden case ``case_multi`` are
+          run sharded and unsharded and compared (``shard_parity``).
+``value``       : cell.gene negative-binomial evaluations per second (cells x genes x steps/s; S and U count as one), counts
+                  resident in HBM (as the reference keeps them: preprocessing.py:193-194).
+``e2e``         : the same step when the count matrices start each step in pinned HOST memory and are copied to the device
+                  inside the timed region, plus the device->host read of the loss.
+``roofline``    : the streaming kernel's algorithmic bytes (8 B per cell.gene: one fp32 S and U each) over its CUDA-event
+                  duration, against the measured HBM peak of MEASURED_PEAKS.json.
+``breakdown_ms``: CUDA-event times of the phases of one (un-graphed) step: draws / sample / likelihood / allreduce /
+                  backward / adam.
+``configs``     : (N = 1) the other named configurations: C3 100k x 2k, the per-GPU shard of C5 (62.5k x 5k, 16 batches, 2
+                  conditions), a tutorial-sized 2,000 x 218 H = 1 two-sample fit, and the PHASE model at 1M x 2k with its
+                  own roofline (4 B per cell.gene).
+``cpu_baseline``: the reference op chain (oracle/models.py: unfused (Ng,Nc) einsums + GammaPoisson + autograd under the same
+                  SVI) on the host cores on a bounded sample (20,000 x 2,000), extrapolated linearly
+                  per cell.gene; ``gpu_unfused`` = the same unfused chain on this GPU at 100k x 2k.
 """
 from __future__ import annotations
 
@@ -39,6 +49,7 @@ import torch  # noqa: E402
 
 METRIC = "cell_gene_nb_evals_per_sec"
 UNIT = "cell*gene/s"
+OPT_ARGS = {"lr": 0.03, "lrd": 0.9996, "betas": (0.8, 0.99)}
 
 
 def parse():
@@ -47,23 +58,28 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="N > 1: strong = --total-cells split over the GPUs (default), weak = --cells-per-gpu on each")
     ap.add_argument("--cells-per-gpu", type=int, default=1_000_000)
+    ap.add_argument("--total-cells", type=int, default=2_000_000, help="config C4: the strong-scaling problem")
     ap.add_argument("--genes", type=int, default=2000)
     ap.add_argument("--harmonics", type=int, default=3)
     ap.add_argument("--omega-harmonics", type=int, default=1)
     ap.add_argument("--batches", type=int, default=1)
     ap.add_argument("--conditions", type=int, default=1)
     ap.add_argument("--model-type", default="lrmn", choices=["lrmn", "normal"])
-    ap.add_argument("--cpu-sample-cells", type=int, default=4000)
-    ap.add_argument("--eager", action="store_true", help="time the eager ppl.infer.SVI.step instead of GraphedSVI")
+    ap.add_argument("--cpu-sample-cells", type=int, default=20000)
+    ap.add_argument("--traced", action="store_true", help="GraphedSVI(fast=False): the step traced through the effect handlers")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"synthetic velocity SVI step, {a.cells_per_gpu} cells x {a.genes} genes per GPU, H={a.harmonics}, "
-            f"Hw={a.omega_harmonics}, Nb={a.batches}, Nx={a.conditions}, guide={a.model_type}")
+def workload_name(cells, genes, a, model="velocity", Nb=None, Nx=None, H=None):
+    return (f"synthetic {model} SVI step, {cells} cells x {genes} genes, H={a.harmonics if H is None else H}, "
+            f"Hw={a.omega_harmonics}, Nb={a.batches if Nb is None else Nb}, Nx={a.conditions if Nx is None else Nx}"
+            + (f", guide={a.model_type}" if model == "velocity" else ""))
 
 
 def priors_from(d, device):
@@ -80,10 +96,10 @@ def priors_from(d, device):
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the reference op chain on the host cores
+# reference op chain (oracle/models.py) under the same SVI: the CPU arm and the "unfused ATen on this GPU" comparator
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(a, n_cells, steps, warmup):
-    """SVI steps of the unfused reference chain on the CPU over ``n_cells`` cells of the workload."""
+def reference_chain_steps(a, n_cells, steps, warmup, device="cpu"):
+    """Seconds per SVI step of the unfused reference chain over ``n_cells`` cells of the workload on ``device``."""
     from oracle import models as omodels
     from velocycle_b200 import ppl as pyro
     from velocycle_b200.ppl.infer import SVI, Trace_ELBO
@@ -92,23 +108,28 @@ def cpu_reference_steps(a, n_cells, steps, warmup):
     from velocycle_b200.synthetic import make_synthetic
 
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    if device == "cpu":
+        torch.set_num_threads(cores)
     d = make_synthetic(n_cells, a.genes, H=a.harmonics, Hw=a.omega_harmonics, Nb=a.batches, Nx=a.conditions,
-                       seed=0, device="cpu", stats=False)
-    mu_nu, sd_nu, phixy, mu_nw, sd_nw = priors_from(d, "cpu")
+                       seed=0, device=device, stats=False)
+    mu_nu, sd_nu, phixy, mu_nw, sd_nw = priors_from(d, device)
     mp = make_velocity_metaparams(d.S[:, : a.genes], d.U[:, : a.genes], mu_nu, sd_nu, phixy, mu_nw, sd_nw,
                                   batch_id=d.batch_id, cond_id=d.cond_id, Nb=a.batches, Nx=a.conditions,
-                                  count_factor=d.cf, model_type=a.model_type, device="cpu")
+                                  count_factor=d.cf, model_type=a.model_type, device=device)
     model = omodels.velocity_model_unfused_lrmn if a.model_type == "lrmn" else omodels.velocity_model_unfused
     pyro.clear_param_store()
     pyro.set_rng_seed(0)
-    svi = SVI(model, mp.guide_fn, ClippedAdam({"lr": 0.03, "lrd": 0.9996, "betas": (0.8, 0.99)}), Trace_ELBO())
+    svi = SVI(model, mp.guide_fn, ClippedAdam(dict(OPT_ARGS)), Trace_ELBO())
+    sync = (lambda: torch.cuda.synchronize()) if device != "cpu" else (lambda: None)
     for _ in range(warmup):
         svi.step(mp)
+    sync()
     t0 = time.perf_counter()
     for _ in range(steps):
         svi.step(mp)
+    sync()
     dt = (time.perf_counter() - t0) / max(steps, 1)
+    pyro.clear_param_store()
     return dt, cores
 
 
@@ -117,15 +138,17 @@ def run_reference_arm(a):
     if rank != 0:
         return
     n = a.cpu_sample_cells
-    dt, cores = cpu_reference_steps(a, n, a.steps, a.warmup)
+    dt, cores = reference_chain_steps(a, n, a.steps, a.warmup)
     value = n * a.genes / dt
+    cells = a.cells_per_gpu if a.gpus == 1 else a.total_cells
     sample = (f"{n} cells x {a.genes} genes of the workload per step (same generator, seed 0), unfused reference op "
-              f"chain + autograd under SVI on the host CPU, {cores} threads")
+              f"chain + autograd under SVI on the host CPU, {cores} threads; cell.gene/s is size-independent, so the value "
+              "stands for the full workload (extrapolated linearly, BASELINE.md section 3)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": sample},
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak" if a.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(cells, a.genes, a), "sample": sample, "extrapolated": True},
         "svi_steps_per_sec_on_sample": 1.0 / dt,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -137,7 +160,7 @@ def run_reference_arm(a):
 # helpers for the GPU arm
 # ------------------------------------------------------------------------------------------------------
 class CudaEvents:
-    """Raw cudaEvent_t pairs (the C ABI records them around the streaming kernel)."""
+    """Raw cudaEvent_t pair (the C ABI records it around the streaming kernel, as event-record nodes inside a graph)."""
 
     def __init__(self):
         self.rt = None
@@ -212,16 +235,251 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def dram_traffic_per_cell_gene():
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "stream_kernel_dram_bytes.json")))
+        return float(prof.get("dram_bytes_per_cell_gene", 0)) or None
+    except Exception:
+        return None
+
+
+OUR_KERNELS_FAST = ("vcb_svi_cell_sample, vcb_svi_gene_sample, vcb_cell_tables, vcb_stream2, vcb_cell_epilogue, "
+                    "vcb_gene_epilogue, vcb_svi_cell_backward, vcb_svi_gene_backward, vcb_svi_finalize, vcb_adam_tick, "
+                    "vcb_clipped_adam")
+
+
+class Workload:
+    """One model on one synthetic dataset on this rank: data, metaparameters, the fit driver and its step function."""
+
+    def __init__(self, a, Nc, Ng, dev, rank=0, world=1, model="velocity", Nb=None, Nx=None, H=None, data=None):
+        from velocycle_b200 import ppl as pyro
+        from velocycle_b200.phase_inference_model import PhaseFitModel
+        from velocycle_b200.ppl.optim import ClippedAdam
+        from velocycle_b200.preprocessing import make_phase_metaparams, make_velocity_metaparams
+        from velocycle_b200.sharding import ShardInfo
+        from velocycle_b200.svi import stepper_for
+        from velocycle_b200.synthetic import make_synthetic
+        from velocycle_b200.velocity_inference_model import VelocityFitModel
+        import torch.distributed as dist
+
+        Nb = a.batches if Nb is None else Nb
+        Nx = a.conditions if Nx is None else Nx
+        H = a.harmonics if H is None else H
+        self.Nc, self.Ng, self.world, self.model, self.dev = Nc, Ng, world, model, dev
+        shard = ShardInfo(rank, world, rank * Nc, Nc * world) if world > 1 else None
+        # every rank draws its own cell shard on its own device (seed = base + rank); priors of the replicated gene-level
+        # parameters come from rank 0
+        d = data if data is not None else make_synthetic(Nc, Ng, H=H, Hw=a.omega_harmonics, Nb=Nb, Nx=Nx,
+                                                         seed=(1000 + rank) if world > 1 else 0, device=dev, stats=True)
+        mu_nu, sd_nu, phixy, mu_nw, sd_nw = priors_from(d, dev)
+        if world > 1:
+            for t in (mu_nu, sd_nu, mu_nw, sd_nw):
+                dist.broadcast(t, src=0)
+        if model == "velocity":
+            self.mp = make_velocity_metaparams(d.S[:, :Ng], d.U[:, :Ng], mu_nu, sd_nu, phixy, mu_nw, sd_nw,
+                                               batch_id=d.batch_id, cond_id=d.cond_id, Nb=Nb, Nx=Nx, count_factor=d.cf,
+                                               model_type=a.model_type, device=dev, shard=shard)
+            self.driver = VelocityFitModel(self.mp, get_posterior=False)
+        else:
+            self.mp = make_phase_metaparams(d.S[:, :Ng], None, mu_nu, sd_nu, phixy, batch_id=d.batch_id, Nb=Nb,
+                                            count_factor=d.cf, device=dev, shard=shard)
+            self.driver = PhaseFitModel(self.mp, get_posterior=False)
+        self.zero_S, self.zero_U = getattr(d, "zero_frac_S", None), getattr(d, "zero_frac_U", None)
+        self.counts = self.mp.packed_counts
+        self.ev = CudaEvents()
+        self.counts.profile_events = self.ev.handles()
+        pyro.clear_param_store()
+        pyro.set_rng_seed(0)  # same seed on every rank: replicated draws agree, per-cell noise is the rank's slice
+        self.optimizer = ClippedAdam(dict(OPT_ARGS))
+        if a.traced:
+            from velocycle_b200.svi import GraphedSVI
+
+            self.gsvi = GraphedSVI(self.driver.model, self.driver.guide, dict(OPT_ARGS), self.mp, fast=False)
+            self.step = self.gsvi.step
+        else:
+            self.step = stepper_for(self.driver, self.driver.model, self.driver.guide, self.optimizer, None, self.mp)
+            self.gsvi = self.step.__self__
+        self.n_mat = 2 if model == "velocity" else 1
+
+    def barrier(self):
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def time_steps(self, steps, warmup, fn=None):
+        """ms per step (CUDA events, MAX over ranks) and the streaming kernel's mean event duration on this rank."""
+        import torch.distributed as dist
+
+        fn = fn or self.step
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kern = []
+        e0.record()
+        for _ in range(steps):
+            fn()  # returns the loss as a Python float: one D2H read + sync per step, as pyro.infer.SVI.step does
+            kern.append(self.ev.elapsed_ms())
+        e1.record()
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kern = [k for k in kern if k == k]
+        return float(t.item()) / steps, (sum(kern) / len(kern) if kern else float("nan"))
+
+    def roofline(self, kern_ms):
+        bytes_per = 4.0 * self.n_mat
+        alg = bytes_per * self.Nc * self.Ng + 4.0 * self.Nc * 8  # fp32 counts once; per-cell inputs / outputs are < 0.1 %
+        peak, src = hbm_peak()
+        achieved = alg / (kern_ms * 1e-3) / 1e9 if kern_ms == kern_ms and kern_ms > 0 else None
+        tr = dram_traffic_per_cell_gene()
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None,
+                "traffic": (tr * self.Nc * self.Ng * self.n_mat / 2.0) if tr else None,
+                "kernel": "vcb_stream2_kernel", "kernel_ms": kern_ms, "algorithmic_bytes": alg, "peak_source": src,
+                "bytes_per_cell_gene": bytes_per}
+
+    def breakdown(self, reps=5):
+        """CUDA-event times of the phases of an un-graphed fused step (mean of ``reps``), ms."""
+        g = self.gsvi
+        if getattr(g, "_fast", None) is None:
+            return None
+        names = ["draws", "sample", "likelihood", "allreduce", "backward", "adam"]
+        acc = {n: 0.0 for n in names}
+        for r in range(reps + 1):
+            evs = [torch.cuda.Event(enable_timing=True)]
+            evs[0].record()
+
+            def mark(_name):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append(e)
+
+            g._fast.body(mark)
+            g._adam()
+            mark("adam")
+            torch.cuda.synchronize()
+            if r:  # the first repetition warms the un-graphed path
+                for i, n in enumerate(names):
+                    acc[n] += evs[i].elapsed_time(evs[i + 1]) / reps
+        acc["stream_kernel"] = self.ev.elapsed_ms()
+        return acc
+
+    def close(self):
+        from velocycle_b200 import ppl as pyro
+
+        self.driver._steppers = {}
+        self.gsvi = self.step = self.driver = self.mp = self.counts = None
+        pyro.clear_param_store()
+        torch.cuda.empty_cache()
+
+
+def shard_parity(dev, rank, world):
+    """6 steps of the golden case `case_multi` (velocity, LRMN guide, 4 batches, 2 conditions) cell-sharded over the ranks
+    against the same fit unsharded (run redundantly on every rank): parameters must agree (5e-3 absolute, the tolerance of
+    tests/test_sharding_gpu.py -- ClippedAdam's normalised update amplifies last-bit gradient differences)."""
+    import numpy as np
+    import torch.distributed as dist
+
+    from velocycle_b200 import ppl as pyro
+    from velocycle_b200.preprocessing import make_velocity_metaparams
+    from velocycle_b200.sharding import ShardInfo, shard_cells
+    from velocycle_b200.svi import GraphedSVI
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "case_multi.npz"), allow_pickle=False)
+    inp = {k[3:]: torch.as_tensor(z[k].astype(np.int64) if z[k].dtype == np.uint16 else z[k]) for k in z.files
+           if k.startswith("in/")}
+    Nc = inp["S"].shape[0]
+
+    def fit(a, b, shard):
+        sl = slice(a, b)
+        mp = make_velocity_metaparams(inp["S"][sl], inp["U"][sl], inp["mu_nu"], inp["sd_nu"], inp["phixy_prior"][sl],
+                                      inp["mu_nw"], inp["sd_nw"], batch_id=inp["batch_id"][sl], cond_id=inp["cond_id"][sl],
+                                      Nb=int(inp["Nb"]), Nx=int(inp["Nx"]), count_factor=inp["cf"][sl], model_type="lrmn",
+                                      device=dev, shard=shard)
+        pyro.clear_param_store()
+        pyro.set_rng_seed(2024)
+        g = GraphedSVI(mp.model_fn, mp.guide_fn, {"lr": 0.03, "lrd": 0.999, "betas": (0.8, 0.99)}, mp, use_graph=False)
+        losses = [g.step() for _ in range(6)]
+        return losses, {k: v.detach().clone() for k, v in pyro.get_param_store().named_parameters()}
+
+    a, b = shard_cells(Nc, rank, world)
+    l_sh, p_sh = fit(a, b, ShardInfo.make(Nc))
+    l_one, p_one = fit(0, Nc, None)
+    worst = 0.0
+    for name, ref in p_one.items():
+        got = p_sh[name]
+        if name == "ϕxy_locs":
+            ref = ref[a:b]
+        finite = torch.isfinite(ref)
+        if finite.any():
+            worst = max(worst, float((got[finite] - ref[finite]).abs().max()))
+    loss_rel = max(abs(x - y) / abs(y) for x, y in zip(l_sh, l_one))
+    t = torch.tensor([worst, loss_rel], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pyro.clear_param_store()
+    return {"max_abs": float(t[0]), "loss_max_rel": float(t[1]), "ok": bool(t[0] <= 5e-3 and t[1] <= 1e-4), "steps": 6,
+            "case": "tests/golden/case_multi.npz, velocity LRMN", "tolerance": "parameters 5e-3 abs, losses 1e-4 rel"}
+
+
+def e2e_run(w, a, n_steps):
+    """The step with both count matrices starting in pinned host memory (HostCounts staging formats), copies inside the timed
+    region (the copy of step i+1 runs on a copy stream under step i), widened on the device, loss read back."""
+    import psutil
+    import torch.distributed as dist
+
+    from velocycle_b200.fused import HostCounts
+
+    counts, dev = w.counts, w.dev
+    hS = HostCounts.from_tensor(counts.S, sub_byte=True)
+    hU = HostCounts.from_tensor(counts.U, sub_byte=True)
+    h2d = hS.nbytes + hU.nbytes
+    if h2d * w.world * 2 > psutil.virtual_memory().available:
+        raise MemoryError("pinned host staging does not fit in host RAM")
+    S_check = counts.S[:4096].clone()
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def start_copies():
+        hS.start_upload(dev, copy_stream)
+        hU.start_upload(dev, copy_stream)
+
+    def steps(k):
+        start_copies()
+        for i in range(k):
+            hS.finish_upload(counts.S)
+            hU.finish_upload(counts.U)
+            if i + 1 < k:
+                start_copies()
+            w.step()
+
+    steps(2)
+    assert torch.equal(S_check, counts.S[:4096]), "HostCounts round trip changed the counts"
+    w.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps(n_steps)
+    e1.record()
+    w.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if w.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / n_steps
+    fmt = {1: "u8 + overflow list", 2: "u16", 4: "i32", 16: "2-bit codes + escape bytes", 32: "4-bit codes + escape bytes",
+           64: "2-bit codes + escape nibbles + escape bytes"}
+    return {"value": w.Nc * w.world * w.Ng / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": 4, "steps": n_steps,
+            "note": (f"S and U copied from pinned host memory every step (HostCounts: S {fmt[hS.fmt]}, U {fmt[hU.fmt]}), widened on "
+                     "the device by vcb_expand_counts*, then one step with the loss read back; PCIe-bound")}
+
+
 # ------------------------------------------------------------------------------------------------------
 def run_ours(a):
     import torch.distributed as dist
 
-    from velocycle_b200 import ppl as pyro
-    from velocycle_b200.ppl.infer import SVI, Trace_ELBO
-    from velocycle_b200.ppl.optim import ClippedAdam
-    from velocycle_b200.preprocessing import make_velocity_metaparams
-    from velocycle_b200.sharding import ShardInfo, init_from_env
-    from velocycle_b200.synthetic import make_synthetic
+    from velocycle_b200.sharding import init_from_env
     import __graft_entry__ as ge
 
     rank, world, local_rank = init_from_env()
@@ -233,189 +491,114 @@ def run_ours(a):
     dev = torch.device("cuda", local_rank)
     if rank == 0:
         ge.build()
-    log = (lambda *m: print(f"[bench rank {rank}]", *m, file=sys.stderr, flush=True)) if os.environ.get("VCB_BENCH_VERBOSE") else (lambda *m: None)
-    log("built")
     if world > 1:
         dist.barrier()
-    log("first barrier passed")
+    scaling = a.scaling if a.scaling != "auto" else ("strong" if world > 1 else "weak")
+    Ng = a.genes
+    Nc = a.cells_per_gpu if (world == 1 or scaling == "weak") else a.total_cells // world
 
-    Nc, Ng = a.cells_per_gpu, a.genes
-    shard = ShardInfo(rank, world, rank * Nc, Nc * world) if world > 1 else None
-    # data: every rank draws its own cell shard on its own device; gene-level truth is shared (same seed)
-    d = make_synthetic(Nc, Ng, H=a.harmonics, Hw=a.omega_harmonics, Nb=a.batches, Nx=a.conditions,
-                       seed=0, device=dev, stats=True)
-    if world > 1:  # different cells per rank, same genes: redraw the cell-level part with a rank-specific seed
-        d2 = make_synthetic(Nc, Ng, H=a.harmonics, Hw=a.omega_harmonics, Nb=a.batches, Nx=a.conditions,
-                            seed=1000 + rank, device=dev, stats=True)
-        # keep the shared gene-level parameters of seed 0 by regenerating counts is expensive; instead use d2
-        # wholesale but overwrite nothing: per-rank gene truths differ slightly, priors below come from rank 0
-        d = d2
-    mu_nu, sd_nu, phixy, mu_nw, sd_nw = priors_from(d, dev)
-    if world > 1:  # replicated priors must be identical on every rank
-        for t in (mu_nu, sd_nu, mu_nw, sd_nw):
-            dist.broadcast(t, src=0)
-    mp = make_velocity_metaparams(d.S[:, :Ng], d.U[:, :Ng], mu_nu, sd_nu, phixy, mu_nw, sd_nw,
-                                  batch_id=d.batch_id, cond_id=d.cond_id, Nb=a.batches, Nx=a.conditions,
-                                  count_factor=d.cf, model_type=a.model_type, device=dev, shard=shard)
-    zero_S, zero_U = d.zero_frac_S, d.zero_frac_U
-    log("metaparams ready")
-    del d
-    torch.cuda.empty_cache()
-    counts = mp.packed_counts
-    ev = CudaEvents()
-    counts.profile_events = ev.handles()
+    parity = shard_parity(dev, rank, world) if world > 1 else None
 
-    pyro.clear_param_store()
-    pyro.set_rng_seed(0)  # same seed on every rank: replicated draws agree, per-cell noise is sliced (ShardedNormal)
-    opt_args = {"lr": 0.03, "lrd": 0.9996, "betas": (0.8, 0.99)}
-    if a.eager:
-        eager = SVI(mp.model_fn, mp.guide_fn, ClippedAdam(opt_args), Trace_ELBO())
-        svi_step = lambda: eager.step(mp)
-        launches_per_step, api = 4, "ppl.infer.SVI.step (eager)"
-    else:
-        from velocycle_b200.svi import GraphedSVI
-
-        graphed = GraphedSVI(mp.model_fn, mp.guide_fn, opt_args, mp)
-        svi_step = lambda: graphed.step()
-        launches_per_step, api = 6, "svi.GraphedSVI.step (CUDA graph)"
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    # ---- the headline workload ---------------------------------------------------------------------------------------
+    w = Workload(a, Nc, Ng, dev, rank, world)
     sampler, path = start_clock_sampler(local_rank) if rank == 0 else (None, None)
-    for _ in range(a.warmup):
-        svi_step()
-    barrier()
-    log("warm-up done")
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
-    e0.record()
-    for _ in range(a.steps):
-        svi_step()  # returns the loss as a Python float: one D2H read + sync per step, as in the reference
-        kern_ms.append(ev.elapsed_ms())
-    e1.record()
-    barrier()
+    ms_per_step, kern = w.time_steps(a.steps, a.warmup)
     clocks = stop_clock_sampler(sampler, path) if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / a.steps
     value = Nc * world * Ng / (ms_per_step * 1e-3)
-
-    # ---- roofline of the streaming kernel (rank 0's launches; every rank runs the same shape) ----------
-    kms = sorted(k for k in kern_ms if k == k)
-    kern = sum(kms) / len(kms) if kms else float("nan")
-    alg_bytes = 8.0 * Nc * Ng + 4.0 * Nc * 8  # fp32 S and U once; per-cell inputs/outputs are < 0.1 %
-    peak, peak_src = hbm_peak()
-    achieved = alg_bytes / (kern * 1e-3) / 1e9 if kern == kern and kern > 0 else None
-    traffic = None
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "stream_kernel_dram_bytes.json")))
-        traffic = prof.get("dram_bytes_per_cell_gene", 0) * Nc * Ng or None
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": ("vcb_umma_stream_kernel (tcgen05, VCB_STREAM_KERNEL=umma)"
-                           if os.environ.get("VCB_STREAM_KERNEL", "").startswith("u") else "vcb_stream_kernel"), "kernel_ms": kern, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
-                "note": "latency / issue-slot bound at 16 warps per SM, not HBM bound: every pipe is < 40 % busy (DESIGN.md section 4, profiles/)"}
-
-    # ---- e2e: counts start every step in pinned host memory ----------------------------------------------
+    roofline = w.roofline(kern)
+    roofline["note"] = ("issue-slot / latency bound at 16 warps per SM, not HBM bound: no pipe above 46 % busy (DESIGN.md "
+                        "section 4, profiles/r02_stream_kernel_ncu_summary.txt)")
+    breakdown = w.breakdown()
+    zero_S, zero_U = w.zero_S, w.zero_U
     e2e = None
     if not a.no_e2e:
         try:
-            import psutil
-
-            from velocycle_b200.fused import HostCounts
-
-            # The step's inputs start in pinned host memory in the narrowest exact integer format (HostCounts: 2- or 4-bit
-            # codes with an escape byte stream, or one byte per count; large counts as an (index, value) list); each e2e
-            # step copies them to the device, widens them into the float32 [Nc][ld] matrices (vcb_expand_counts[_packed])
-            # and runs the SVI step on them.
-            hS = HostCounts.from_tensor(counts.S, sub_byte=True)
-            hU = HostCounts.from_tensor(counts.U, sub_byte=True)
-            h2d = hS.nbytes + hU.nbytes
-            need = h2d
-            avail = psutil.virtual_memory().available
-            if need * world * 2 > avail:
-                raise MemoryError(f"{need * world} B of pinned host staging do not fit in {avail} B of host RAM")
-            S_check = counts.S[:4096].clone()
-            n_e2e = max(2, min(a.steps, 10))
-            # Every step's inputs cross PCIe inside the timed region.  The copies run on a second stream into the spare
-            # set of device staging buffers (HostCounts.start_upload), so the copy of step i+1 overlaps the SVI step i --
-            # what any input pipeline does; the first copy of the region is not overlapped with anything.
-            copy_stream = torch.cuda.Stream(device=dev)
-            def start_copies():
-                hS.start_upload(dev, copy_stream)
-                hU.start_upload(dev, copy_stream)
-            def e2e_steps(k):
-                start_copies()
-                for i in range(k):
-                    hS.finish_upload(counts.S)
-                    hU.finish_upload(counts.U)
-                    if i + 1 < k:
-                        start_copies()
-                    svi_step()
-            e2e_steps(2)
-            assert torch.equal(S_check, counts.S[:4096]), "HostCounts round trip changed the counts"
-            barrier()
-            e0.record()
-            e2e_steps(n_e2e)
-            e1.record()
-            barrier()
-            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item()) / n_e2e
-            fmt_name = {1: "u8 + overflow list", 2: "u16", 4: "i32", 16: "2-bit codes + escape bytes + overflow list",
-                        32: "4-bit codes + escape bytes + overflow list",
-                        64: "2-bit codes + escape nibbles + escape bytes + overflow list"}
-            e2e = {"value": Nc * world * Ng / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "steps": n_e2e,
-                   "note": ("both count matrices copied from pinned host memory every step in the staging format of "
-                            f"velocycle_b200.fused.HostCounts (S: {fmt_name[hS.fmt]}, U: {fmt_name[hU.fmt]}; "
-                            f"{(0 if hS.over_idx is None else hS.over_idx.numel()) + (0 if hU.over_idx is None else hU.over_idx.numel())}"
-                            " entries in the overflow lists), widened on the device to the float32 layout by vcb_expand_counts[_packed], "
-                            "then one GraphedSVI step with the loss read back; the copies of step i+1 run on a copy stream under step i")}
-            del hS, hU
+            e2e = e2e_run(w, a, max(2, min(a.steps, 10)))
         except Exception as exc:  # pragma: no cover
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
+    fast = getattr(w.gsvi, "_fast", None) is not None
+    w.close()
 
-    # ---- CPU baseline on rank 0 at N = 1 --------------------------------------------------------------------
-    cpu = None
+    # ---- N > 1: the weak-scaling figure next to the strong one ---------------------------------------------------------
+    weak = None
+    if world > 1 and scaling == "strong" and a.cells_per_gpu != Nc:
+        ww = Workload(a, a.cells_per_gpu, Ng, dev, rank, world)
+        ms_w, kern_w = ww.time_steps(max(5, a.steps // 2), a.warmup)
+        weak = {"scaling": "weak", "cells_per_gpu": a.cells_per_gpu, "ms_per_step": ms_w, "kernel_ms": kern_w,
+                "value": a.cells_per_gpu * world * Ng / (ms_w * 1e-3), "unit": UNIT, "breakdown_ms": ww.breakdown()}
+        ww.close()
+
+    # ---- N = 1: the other named configurations, the unfused chain on this GPU, the CPU arm --------------------------------
+    configs, cpu = None, None
+    if world == 1 and not a.no_configs:
+        configs = {}
+        specs = [
+            ("C3_100k_x_2k", dict(Nc=100_000, Ng=2000, model="velocity")),
+            ("C5_shard_62500_x_5k_Nb16_Nx2", dict(Nc=62_500, Ng=5000, model="velocity", Nb=16, Nx=2)),
+            ("tutorial_2000_x_218_H1_Nb2_Nx2", dict(Nc=2000, Ng=218, model="velocity", Nb=2, Nx=2, H=1)),
+            ("phase_1M_x_2k", dict(Nc=a.cells_per_gpu, Ng=2000, model="phase")),
+        ]
+        for name, kw in specs:
+            try:
+                c = Workload(a, kw["Nc"], kw["Ng"], dev, model=kw["model"], Nb=kw.get("Nb"), Nx=kw.get("Nx"), H=kw.get("H"))
+                ms_c, kern_c = c.time_steps(a.steps, a.warmup)
+                rl = c.roofline(kern_c)
+                if kw["model"] == "phase":
+                    rl["note"] = "phase model: 4 B and 3 MUFU per cell.gene (S only): the same issue-slot bound, half the bytes"
+                configs[name] = {"workload": workload_name(kw["Nc"], kw["Ng"], a, kw["model"], kw.get("Nb"), kw.get("Nx"), kw.get("H")),
+                                 "ms_per_step": ms_c, "svi_steps_per_sec": 1e3 / ms_c,
+                                 "value": kw["Nc"] * kw["Ng"] / (ms_c * 1e-3), "unit": UNIT, "kernel_ms": kern_c,
+                                 "roofline_frac": rl["frac"], "roofline": rl, "breakdown_ms": c.breakdown()}
+                c.close()
+            except Exception as exc:  # pragma: no cover
+                configs[name] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             n = a.cpu_sample_cells
-            dt, cores = cpu_reference_steps(a, n, steps=4, warmup=1)
-            cpu = {"value": n * Ng / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{n} cells x {Ng} genes of the same workload, 1 warm-up + 4 timed SVI steps of the "
-                             f"unfused reference op chain (oracle/models.py) on the host CPU",
+            dt, cores = reference_chain_steps(a, n, steps=4, warmup=1)
+            cpu = {"value": n * Ng / dt, "unit": UNIT, "cores": cores, "kind": "port", "extrapolated": True,
+                   "sample": f"{n} cells x {Ng} genes of the same workload, 1 warm-up + 4 timed SVI steps of the unfused "
+                             "reference op chain (oracle/models.py) on the host CPU; linear in cells, so the value stands for "
+                             "the full workload",
                    "ms_per_step_on_sample": dt * 1e3}
+            try:  # the same unfused ATen chain on this GPU at 100k x 2k
+                n_gpu = 100_000
+                dtg, _ = reference_chain_steps(a, n_gpu, steps=3, warmup=1, device=dev)
+                cpu["gpu_unfused"] = {"value": n_gpu * Ng / dtg, "unit": UNIT, "ms_per_step": dtg * 1e3,
+                                      "sample": f"{n_gpu} cells x {Ng} genes, the same unfused chain (eager SVI) on this B200"}
+            except Exception as exc:  # pragma: no cover
+                cpu["gpu_unfused"] = {"error": repr(exc)}
         except Exception as exc:  # pragma: no cover
             cpu = {"value": None, "error": repr(exc)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "cells_total": Nc * world, "genes": Ng, "n_mat": 2,
-                       "l2_flush": "not needed: 16 GB of counts per step >> 126 MB L2",
+            "config": {"workload": workload_name(Nc * world, Ng, a), "cells_total": Nc * world, "cells_per_gpu": Nc,
+                       "genes": Ng, "n_mat": 2,
+                       "l2_flush": f"not needed: {8e-9 * Nc * Ng:.1f} GB of counts per GPU and step >> 126 MB L2",
                        "zero_fraction_S": zero_S, "zero_fraction_U": zero_U, "parallelism": f"cell-shard x{world}"},
             "svi_steps_per_sec": 1e3 / ms_per_step,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": a.steps * launches_per_step,
-            "gpu_launches_note": "our kernels per step: vcb_cell_tables, vcb_stream_kernel, vcb_cell_epilogue, "
-                                 "vcb_gene_epilogue (+ vcb_adam_tick, vcb_clipped_adam under GraphedSVI)",
-            "api": api,
+            "roofline": roofline, "breakdown_ms": breakdown, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": a.steps * (11 if fast else 6),
+            "gpu_launches_note": ("our kernels per step: " + OUR_KERNELS_FAST) if fast else
+                                 "our kernels per step: vcb_cell_tables, vcb_stream2, vcb_cell_epilogue, vcb_gene_epilogue, "
+                                 "vcb_adam_tick, vcb_clipped_adam (the rest of the traced step is torch)",
+            "api": "the step function of VelocityFitModel.fit (svi.stepper_for -> GraphedSVI.step, one CUDA graph per step"
+                   + (", fused step)" if fast else ", traced step)"),
         }
+        if weak is not None:
+            line["weak"] = weak
+        if parity is not None:
+            line["shard_parity"] = parity
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
     if world > 1:
-        # NCCL communicators referenced by a captured CUDA graph do not tear down cleanly
-        # (destroy_process_group blocks); everything is printed, so leave without the teardown
+        # NCCL communicators referenced by a captured CUDA graph do not tear down cleanly (destroy_process_group blocks);
+        # everything is printed, so leave without the teardown
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
@@ -427,7 +610,7 @@ def main():
     import faulthandler
 
     # never hang a GPU box: dump every thread's stack and exit if the run exceeds the watchdog
-    faulthandler.dump_traceback_later(int(os.environ.get("VCB_BENCH_WATCHDOG_S", "900")), exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get("VCB_BENCH_WATCHDOG_S", "1200")), exit=True)
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)

@@ -221,11 +221,18 @@ class FusedStep:
             setattr(p, k, t.data_ptr())
         self.eps = e  # alive until the step's kernels have run (and the graph's private pool keeps the addresses)
 
-    def body(self) -> None:
-        """Enqueue one step on the current stream (graph capturable)."""
+    def body(self, mark=None) -> None:
+        """Enqueue one step on the current stream (graph capturable).  ``mark(name)`` is called at the phase boundaries
+        (bench.py records CUDA events there: draws / sample / likelihood / allreduce / backward)."""
+        mark = mark or (lambda name: None)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         self._draw()
+        mark("draws")
         _lib.check(self.lib.vcb_svi_sample(C.byref(self.p), st), "vcb_svi_sample")
+        mark("sample")
         _lib.check(self.like_fn(C.byref(self.q), self.ws.data_ptr(), self.ws_bytes, st), "likelihood")
+        mark("likelihood")
         allreduce_flat_(self.gene_flat, self.shard)
+        mark("allreduce")
         _lib.check(self.lib.vcb_svi_backward(C.byref(self.p), st), "vcb_svi_backward")
+        mark("backward")
