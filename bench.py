@@ -47,6 +47,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+_RESULT_FD = 1
 METRIC = "cell_gene_nb_evals_per_sec"
 UNIT = "cell*gene/s"
 OPT_ARGS = {"lr": 0.03, "lrd": 0.9996, "betas": (0.8, 0.99)}
@@ -153,7 +154,11 @@ def run_reference_arm(a):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line) -> None:
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -595,7 +600,7 @@ def run_ours(a):
             line["shard_parity"] = parity
         if configs is not None:
             line["configs"] = configs
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # NCCL communicators referenced by a captured CUDA graph do not tear down cleanly (destroy_process_group blocks);
         # everything is printed, so leave without the teardown
@@ -608,6 +613,13 @@ def run_ours(a):
 
 def main():
     import faulthandler
+
+    # stdout carries exactly ONE line, the JSON result: everything else that writes to file descriptor 1 (NCCL's version
+    # banner, library chatter) is sent to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
 
     # never hang a GPU box: dump every thread's stack and exit if the run exceeds the watchdog
     faulthandler.dump_traceback_later(int(os.environ.get("VCB_BENCH_WATCHDOG_S", "1200")), exit=True)
