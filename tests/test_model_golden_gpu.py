@@ -179,3 +179,32 @@ def test_graphed_svi_matches_eager_svi(kind, use_graph):
         got = pyro.get_param_store().get_unconstrained(name).detach()
         finite = torch.isfinite(ref)
         assert float((got[finite] - ref[finite]).abs().max()) <= 5e-3, name
+
+
+@pytest.mark.parametrize("kind", ["phase", "velocity_lrmn"])
+def test_posterior_draws_touch_no_counts_and_equal_predictive(kind, monkeypatch):
+    """``sample_posterior`` with latent / deterministic ``return_sites`` (what ``fit`` asks for, velocity_inference_model.py:
+    213-224): same seed => the same tensors as a plain ``Predictive`` over the full model, but the fused likelihood is never
+    called (the reference re-evaluates the S / U sites over the (Ng, Nc) matrices for each of the 500 draws)."""
+    from velocycle_b200 import phase_inference_model as pm, ppl as pyro, velocity_inference_model as vm
+    from velocycle_b200.ppl.infer import Predictive
+
+    z, inp = load("case_stereo")
+    mp = _mp(inp, kind)
+    mod = pm if kind == "phase" else vm
+    driver = (pm.PhaseFitModel if kind == "phase" else vm.VelocityFitModel)(mp, get_posterior=False)
+    rs = ["ν", "ϕxy", "ϕ", "ζ", "shape_inv", "Δν"] if kind == "phase" else driver._return_sites()
+    pyro.clear_param_store()
+    pyro.set_rng_seed(9)
+    ref = {k: v.cpu() for k, v in Predictive(driver.model, guide=driver.guide, num_samples=3, return_sites=rs)(mp).items()}
+    calls = []
+    real = mod.fused_cycle_nb
+    monkeypatch.setattr(mod, "fused_cycle_nb", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    pyro.set_rng_seed(9)
+    got = driver.sample_posterior(num_samples=3, rs=rs)
+    assert not calls
+    assert set(got) == set(ref)
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), k
+    driver.sample_posterior(num_samples=1, rs=None)  # the default (every latent site) keeps the full model
+    assert calls

@@ -17,7 +17,31 @@ from torch.distributions import constraints
 from . import _lib
 from .fused import PackedCounts
 
-__all__ = ["FusedCountLikelihood", "packed_counts_for", "attach_packed_counts"]
+__all__ = ["FusedCountLikelihood", "packed_counts_for", "attach_packed_counts", "without_count_sites", "count_sites_enabled"]
+
+_COUNT_SITES = True
+
+
+class without_count_sites:
+    """Context manager: the model functions of this package skip their observed count sites ("S", "U") -- the fused
+    likelihood pass over the count matrices -- while it is active.  The fit drivers use it for posterior draws
+    (``Predictive`` with ``return_sites`` that name latent / deterministic sites only, ``velocity_inference_model.py:213-224``):
+    the reference re-evaluates both GammaPoisson sites over the (Ng, Nc) matrices for each of the 500 draws although nobody
+    reads them; here a draw touches no count byte."""
+
+    def __enter__(self):
+        global _COUNT_SITES
+        self._prev, _COUNT_SITES = _COUNT_SITES, False
+        return self
+
+    def __exit__(self, *exc):
+        global _COUNT_SITES
+        _COUNT_SITES = self._prev
+        return False
+
+
+def count_sites_enabled() -> bool:
+    return _COUNT_SITES
 
 _SIDECARS: Dict[Tuple, PackedCounts] = {}
 

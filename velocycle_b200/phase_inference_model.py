@@ -16,7 +16,7 @@ import torch
 
 from ._const import const
 from .fused import fused_cycle_nb
-from .likelihood import FusedCountLikelihood, packed_counts_for
+from .likelihood import FusedCountLikelihood, count_sites_enabled, packed_counts_for, without_count_sites
 from .phase_inference_guide import phase_latent_variable_guide
 from .ppl import backend
 from .utils import pack_direction, torch_fourier_basis
@@ -47,6 +47,8 @@ def phase_latent_variable_model(mp):
 
     with genes:
         shape_inv = pyro.sample("shape_inv", dist.Gamma(mp.gamma_alpha.to(dev), mp.gamma_beta.to(dev)))
+    if not count_sites_enabled():  # posterior draws of latent / deterministic sites: no pass over the counts
+        return
     counts = packed_counts_for(mp, need_U=False)
     lp_S, _ = fused_cycle_nb(
         counts, phi.reshape(-1), mp.count_factor.reshape(-1), nu.reshape(mp.Ng, -1),
@@ -140,19 +142,33 @@ class PhaseFitModel:
             if mp.Ng * mp.Nc <= self.max_dense_elements:
                 from .posterior import expected_log_counts_summary
 
-                nu = pyro.param("ν_locs").detach().cpu().reshape(mp.Ng, -1)
-                dnu = pyro.param("Δν_locs").detach().cpu().reshape(mp.Nb, mp.Ng) if mp.with_delta_nu else None
-                bid = packed_counts_for(mp, need_U=False).batch_id.cpu() if mp.with_delta_nu else None
-                self.posterior.update(expected_log_counts_summary(nu, self.phase_pyro.phis, mp.count_factor.detach().cpu(), dnu, bid))
+                dev = torch.device(mp.device)  # evaluated where the data live (the reference: on the CPU), returned on the CPU
+                nu = pyro.param("ν_locs").detach().to(dev).reshape(mp.Ng, -1)
+                dnu = pyro.param("Δν_locs").detach().to(dev).reshape(mp.Nb, mp.Ng) if mp.with_delta_nu else None
+                bid = self._batch_ids(dev) if mp.with_delta_nu else None
+                phis = torch.as_tensor(self.phase_pyro.phis, dtype=torch.float32).to(dev)
+                summ = expected_log_counts_summary(nu, phis, mp.count_factor.detach().to(dev), dnu, bid)
+                self.posterior.update({k: v.cpu() for k, v in summ.items()})
         if store_output:
             return intermediate_output
+
+    def _batch_ids(self, dev):
+        """Batch id of every cell in the CALLER's cell order (PackedCounts may hold the rows sorted by batch)."""
+        pc = packed_counts_for(self.metaparams, need_U=False)
+        bid = pc.batch_id if pc.perm is None else pc.batch_id[pc.inv_perm]
+        return bid.to(dev)
 
     def sample_posterior(self, num_samples=1, rs=None, mp=None):
         _, _, _, infer, _ = backend.get()
         mp = self.metaparams if mp is None else mp
         pred = infer.Predictive(self.model, guide=self.guide, num_samples=num_samples,
                                 return_sites=() if rs is None else rs)
-        return {k: v.cpu() for k, v in pred(mp).items()}
+        if rs is not None and "S" not in rs:
+            with without_count_sites():
+                out = pred(mp)
+        else:
+            out = pred(mp)
+        return {k: v.cpu() for k, v in out.items()}
 
     def _check_model(self, m, *args):
         pyro, _, poutine, _, _ = backend.get()

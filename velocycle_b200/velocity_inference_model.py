@@ -17,7 +17,7 @@ import torch
 
 from ._const import const
 from .fused import fused_cycle_nb
-from .likelihood import FusedCountLikelihood, packed_counts_for
+from .likelihood import FusedCountLikelihood, count_sites_enabled, packed_counts_for, without_count_sites
 from .ppl import backend
 from .utils import pack_direction, torch_basis
 from .velocity_inference_guide import velocity_latent_variable_guide, velocity_latent_variable_guide_LRMN  # noqa: F401
@@ -70,6 +70,8 @@ def _velocity_model(mp, lrmn: bool):
     # gradient joins the single fused backward
     cid = counts.cond_id.long() if counts.cond_id is not None else torch.zeros(mp.Nc, dtype=torch.long, device=dev)
     pyro.deterministic("ω", (nuw.detach()[cid] * zeta_omega.detach().T).sum(-1).unsqueeze(0))
+    if not count_sites_enabled():  # posterior draws of latent / deterministic sites: no pass over the counts
+        return
     lp_S, lp_U = fused_cycle_nb(
         counts, phi.reshape(-1), mp.count_factor.reshape(-1), nu.reshape(mp.Ng, -1),
         None if dnu is None else dnu.reshape(mp.Nb, mp.Ng), shape_inv.reshape(-1),
@@ -189,14 +191,18 @@ class VelocityFitModel:
                 from .posterior import expected_log_counts_summary
 
                 pc = packed_counts_for(mp, need_U=True)
-                nu = pyro.param("ν_locs").detach().cpu().reshape(mp.Ng, -1)
-                dnu = pyro.param("Δν_locs").detach().cpu().reshape(mp.Nb, mp.Ng) if mp.with_delta_nu else None
-                cid = pc.cond_id.cpu() if pc.cond_id is not None else torch.zeros(mp.Nc, dtype=torch.int32)
-                velo = dict(nu_omega=self.posterior["νω"].mean(0).reshape(mp.Nx, mp.Nhω), cond_id=cid,
-                            gamma=self.posterior["γg"].mean(0).reshape(-1), logbeta=self.posterior["logβg"].mean(0).reshape(-1))
-                self.posterior.update(expected_log_counts_summary(
-                    nu, self.phase_pyro.phis, mp.count_factor.detach().cpu(), dnu,
-                    pc.batch_id.cpu() if mp.with_delta_nu else None, velocity=velo))
+                dev = torch.device(mp.device)  # evaluated where the data live (the reference: on the CPU), returned on the CPU
+                unsort = (lambda t: t) if pc.perm is None else (lambda t: t[pc.inv_perm])  # ids in the caller's cell order
+                nu = pyro.param("ν_locs").detach().to(dev).reshape(mp.Ng, -1)
+                dnu = pyro.param("Δν_locs").detach().to(dev).reshape(mp.Nb, mp.Ng) if mp.with_delta_nu else None
+                cid = unsort(pc.cond_id).to(dev) if pc.cond_id is not None else torch.zeros(mp.Nc, dtype=torch.int32, device=dev)
+                velo = dict(nu_omega=self.posterior["νω"].mean(0).reshape(mp.Nx, mp.Nhω).to(dev), cond_id=cid,
+                            gamma=self.posterior["γg"].mean(0).reshape(-1).to(dev),
+                            logbeta=self.posterior["logβg"].mean(0).reshape(-1).to(dev))
+                phis = torch.as_tensor(self.phase_pyro.phis, dtype=torch.float32).to(dev)
+                summ = expected_log_counts_summary(nu, phis, mp.count_factor.detach().to(dev), dnu,
+                                                   unsort(pc.batch_id).to(dev) if mp.with_delta_nu else None, velocity=velo)
+                self.posterior.update({k: v.cpu() for k, v in summ.items()})
         if store_output:
             return intermediate_output
 
@@ -205,7 +211,12 @@ class VelocityFitModel:
         mp = self.metaparams if mp is None else mp
         pred = infer.Predictive(self.model, guide=self.guide, num_samples=num_samples,
                                 return_sites=() if rs is None else rs)
-        return {k: v.cpu() for k, v in pred(mp).items()}
+        if rs is not None and not ({"S", "U"} & set(rs)):
+            with without_count_sites():
+                out = pred(mp)
+        else:
+            out = pred(mp)
+        return {k: v.cpu() for k, v in out.items()}
 
     def _check_model(self, m, *args):
         pyro, _, poutine, _, _ = backend.get()
