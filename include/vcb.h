@@ -55,8 +55,8 @@ extern "C" {
 #define VCB_FLAG_GRAD 1u          /* also emit every gradient (otherwise log-prob sums only) */
 #define VCB_FLAG_LGAMMA_INLINE 2u /* evaluate lgamma/digamma terms per element instead of via the histogram */
 #define VCB_FLAG_TCGEN05 4u       /* stream with the tcgen05 kernel (vcb_umma.cuh) where it applies: velocity model, VCB_FLAG_GRAD,
-                                     no VCB_FLAG_LGAMMA_INLINE, H <= 3, Nb <= 1; ignored otherwise.  Same results to fp32 rounding;
-                                     the environment variable VCB_STREAM_KERNEL=umma turns it on for every call */
+                                     no VCB_FLAG_LGAMMA_INLINE, H <= 3, Nb <= 1; ignored otherwise.  Same results to fp32 rounding.
+                                     (The library reads no environment variables.) */
 
 #define VCB_FLAG_LEGACY_STREAM 8u  /* stream with the round-1 kernel (vcb_stream.cuh) even where the round-2 kernel applies
                                      (kept for A/B measurements and as the H > 3 / inline-lgamma path) */

@@ -77,3 +77,46 @@ def test_conditioned_model_falls_back_to_the_traced_step():
     g = GraphedSVI(poutine.condition(mp.model_fn, data=cond), poutine.block(mp.guide_fn, hide=["shape_inv"]), dict(ARGS), mp,
                    use_graph=False)
     assert np.isfinite(g.step()) and g._fast is None
+
+
+def test_clipped_adam_propagates_nan_like_torch_clamp():
+    """torch.clamp_ (Pyro's ClippedAdam, the eager path) lets a NaN gradient through; fminf / fmaxf would turn it into
+    -clip and a silently drifting parameter."""
+    from velocycle_b200 import _lib
+
+    lib = _lib.load()
+    n = 1000
+    p = torch.ones(n, device="cuda")
+    g = torch.full((n,), 0.5, device="cuda")
+    g[7] = float("nan")
+    g[8] = 1e9
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    rc = lib.vcb_clipped_adam(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, step.data_ptr(), 0.03, 1.0, 0.8, 0.99,
+                              1e-8, 10.0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.isnan(p[7]) and torch.isfinite(p[8]) and int(step.item()) == 1
+    assert torch.isfinite(torch.cat([p[:7], p[8:]])).all()
+
+
+def test_packed_count_sidecar_follows_the_design_not_the_address():
+    """Metaparameters from the reference's own preprocessing carry no packed counts: they are built on first use and kept on
+    the count tensor.  Another design over the same matrix must not reuse them (the old cache was keyed on the
+    data pointer alone)."""
+    import collections
+
+    from velocycle_b200.likelihood import packed_counts_for
+
+    S = torch.randint(0, 5, (40, 300), device="cuda").float()  # logical (Ng, Nc)
+    U = torch.randint(0, 3, (40, 300), device="cuda").float()
+    MP = collections.namedtuple("MP", "S U Db D")
+    ids1 = torch.arange(300, device="cuda") % 2
+    ids2 = torch.arange(300, device="cuda") % 3
+    hot = lambda ids, n: torch.nn.functional.one_hot(ids, n).T[:, None, :].float()
+    mp1 = MP(S, U, hot(ids1, 2), None)
+    mp2 = MP(S, U, hot(ids2, 3), None)
+    a = packed_counts_for(mp1, need_U=True)
+    assert packed_counts_for(mp1, need_U=True) is a and packed_counts_for(mp1, need_U=False) is a
+    b = packed_counts_for(mp2, need_U=True)
+    assert b is not a and int(b.batch_id.max()) == 2 and int(a.batch_id.max()) == 1

@@ -48,7 +48,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "kernels":
         kernels(int(sys.argv[2]), int(sys.argv[3]))
         sys.exit(0)
-    print("VCB_PAIRS_PER_THREAD =", os.environ.get("VCB_PAIRS_PER_THREAD"))
     for legacy in (False, True):
         run(400_000, 2000, True, legacy=legacy)
         run(400_000, 2000, False, legacy=legacy)

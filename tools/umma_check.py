@@ -1,6 +1,5 @@
-"""Parity report of the tcgen05 streaming kernel (VCB_STREAM_KERNEL=umma) against the fp64 oracle, then a timing run."""
+"""Parity report of the tcgen05 streaming kernel (VCB_FLAG_TCGEN05) against the fp64 oracle."""
 import os, sys
-os.environ["VCB_STREAM_KERNEL"] = "umma"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
@@ -14,7 +13,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "small":
 worst = 0.0
 for (Nc, Ng, H, Hw, Nb, Nx) in shapes:
     d = make_synthetic(Nc, Ng, H=H, Hw=Hw, Nb=Nb, Nx=Nx, seed=3, device="cuda", sorted_batches=True)
-    out, ref, _ = T._run(d, True)
+    out, ref, _ = T._run(d, True, tcgen05=True)
     ref32 = ref.pop("_ref32")
     line = []
     for k, v in ref.items():

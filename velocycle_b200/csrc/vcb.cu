@@ -624,7 +624,7 @@ __global__ void vcb_clipped_adam_kernel(float* __restrict__ p, const float* __re
   const float step_size = (float)(lr * sqrt(bc2) / bc1);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i];
-    gi = fminf(fmaxf(gi, -clip), clip);
+    gi = (gi != gi) ? gi : fminf(fmaxf(gi, -clip), clip);  // torch.clamp_ propagates NaN (fminf / fmaxf would not)
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
@@ -665,13 +665,9 @@ static int check_device() {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int pairs_per_warp() {
-  // NPAIR = 1: 512 threads, a warp owns 32 genes (<=128 regs); NPAIR = 2: 256 threads, 64 genes per warp (<=255 regs)
-  static int np = 0;
-  if (np == 0) {
-    const char* e = getenv("VCB_PAIRS_PER_THREAD");
-    np = (e && e[0] == '2') ? 2 : ((e && e[0] == '1') ? 1 : VCB_DEFAULT_NP);
-  }
-  return np;
+  // NPAIR = 1: 512 threads, a warp owns 32 genes (<=128 regs); NPAIR = 2: 256 threads, 64 genes per warp (<=255 regs).
+  // A build-time choice (-DVCB_DEFAULT_NP=2): the library reads no environment variables.
+  return VCB_DEFAULT_NP;
 }
 
 constexpr int kSmemBudget = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
@@ -785,15 +781,6 @@ struct UmmaPlan {
   size_t off_tabF, off_tabB, off_omega, off_zero, off_genepart, off_cellpart, off_dnwpart, total;
   int n_cell_blocks;
 };
-
-static int stream_kernel_choice() {  // 0 = mma.sync kernel, 1 = tcgen05 kernel where it applies
-  static int c = -1;
-  if (c < 0) {
-    const char* e = getenv("VCB_STREAM_KERNEL");
-    c = (e && e[0] == 'u') ? 1 : 0;
-  }
-  return c;
-}
 
 static bool umma_applies(const vcb_problem_t* p, bool velo) {
   return velo && (p->flags & VCB_FLAG_GRAD) && !(p->flags & VCB_FLAG_LGAMMA_INLINE) && p->H <= 3 && p->Nb <= 1 && p->Nc > 0;
@@ -1094,7 +1081,7 @@ static int run(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_byt
   rc = check_device();
   if (rc != VCB_OK) return rc;
   if (!(p->flags & VCB_FLAG_TCGEN05) && stream2_applies(p)) return run2(p, velo, workspace, ws_bytes, stream);
-  if ((stream_kernel_choice() == 1 || (p->flags & VCB_FLAG_TCGEN05)) && umma_applies(p, velo)) return run_umma(p, workspace, ws_bytes, stream);
+  if ((p->flags & VCB_FLAG_TCGEN05) && umma_applies(p, velo)) return run_umma(p, workspace, ws_bytes, stream);
   const Plan pl = make_plan(p, velo);
   if (ws_bytes < pl.total) return VCB_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1225,15 +1212,18 @@ size_t vcb_workspace_bytes(const vcb_problem_t* p) {
 }
 
 int vcb_phase_fwd_bwd(const vcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
+  vcb::DeviceGuard guard(p ? p->S : nullptr);
   return vcb::run(p, false, workspace, workspace_bytes, stream);
 }
 
 int vcb_velocity_fwd_bwd(const vcb_problem_t* p, void* workspace, size_t workspace_bytes, void* stream) {
+  vcb::DeviceGuard guard(p ? p->S : nullptr);
   return vcb::run(p, true, workspace, workspace_bytes, stream);
 }
 
 int vcb_count_histogram(const float* M, int64_t Nc, int64_t Ng, int64_t ld, int32_t B, uint32_t* hist, int32_t* status,
                         void* stream) {
+  vcb::DeviceGuard guard(M);
   if (!M || !hist || !status) return VCB_ERR_NULL;
   if (Nc < 0 || Ng <= 0 || ld < Ng || B < 2) return VCB_ERR_SIZE;
   if (Nc == 0) return VCB_OK;
@@ -1247,6 +1237,7 @@ int vcb_count_histogram(const float* M, int64_t Nc, int64_t Ng, int64_t ld, int3
 
 int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst, const int64_t* over_idx,
                       const float* over_val, int64_t n_over, void* stream) {
+  vcb::DeviceGuard guard(dst);
   if (!src || !dst) return VCB_ERR_NULL;
   if (n < 0 || n_over < 0) return VCB_ERR_SIZE;
   if (n_over > 0 && (!over_idx || !over_val || src_dtype != VCB_COUNTS_U8)) return VCB_ERR_NULL;
@@ -1254,7 +1245,7 @@ int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst,
   if (n == 0) return VCB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int bs = 256;
-  const unsigned blocks = 148 * 8;
+  const unsigned blocks = (unsigned)vcb::sm_count() * 8;
   switch (src_dtype) {
     case VCB_COUNTS_U8: vcb::vcb_expand_counts_kernel<uint8_t><<<blocks, bs, 0, st>>>((const uint8_t*)src, dst, n); break;
     case VCB_COUNTS_U16: vcb::vcb_expand_counts_kernel<uint16_t><<<blocks, bs, 0, st>>>((const uint16_t*)src, dst, n); break;
@@ -1274,6 +1265,7 @@ int vcb_expand_counts(const void* src, int32_t src_dtype, int64_t n, float* dst,
 
 int vcb_expand_counts_packed(const uint32_t* codes, int32_t bits, const uint8_t* side, const int64_t* block_off, int64_t n,
                              float* dst, const int64_t* over_idx, const float* over_val, int64_t n_over, void* stream) {
+  vcb::DeviceGuard guard(dst);
   if (!codes || !block_off || !dst) return VCB_ERR_NULL;
   if (n < 0 || n_over < 0 || (bits != 2 && bits != 4)) return VCB_ERR_SIZE;
   if (n_over > 0 && (!over_idx || !over_val)) return VCB_ERR_NULL;
@@ -1282,7 +1274,7 @@ int vcb_expand_counts_packed(const uint32_t* codes, int32_t bits, const uint8_t*
   cudaStream_t st = (cudaStream_t)stream;
   const long long per_block = (long long)VCB_PACKED_BLOCK_WORDS * (32 / bits);
   const long long n_blocks = (n + per_block - 1) / per_block;
-  long long grid = n_blocks < 148LL * 16 ? n_blocks : 148LL * 16;
+  long long grid = n_blocks < (long long)vcb::sm_count() * 16 ? n_blocks : (long long)vcb::sm_count() * 16;
   if (bits == 2)
     vcb::vcb_expand_packed_kernel<2><<<(unsigned)grid, VCB_PACKED_BLOCK_WORDS, 0, st>>>(codes, side, (const long long*)block_off, n, n_blocks, dst);
   else
@@ -1292,7 +1284,7 @@ int vcb_expand_counts_packed(const uint32_t* codes, int32_t bits, const uint8_t*
   if (n_over > 0) {
     const int bs = 256;
     long long b = (n_over + bs - 1) / bs;
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > vcb::sm_count() * 8) b = vcb::sm_count() * 8;
     vcb::vcb_scatter_overflow_kernel<<<(unsigned)b, bs, 0, st>>>((const long long*)over_idx, over_val, n_over, dst);
     e = cudaGetLastError();
   }
@@ -1302,6 +1294,7 @@ int vcb_expand_counts_packed(const uint32_t* codes, int32_t bits, const uint8_t*
 int vcb_expand_counts_twolevel(const uint32_t* codes, const uint32_t* nibbles, const uint8_t* side, const int64_t* block_off1,
                               const int64_t* block_off2, int64_t n, float* dst, const int64_t* over_idx, const float* over_val,
                               int64_t n_over, void* stream) {
+  vcb::DeviceGuard guard(dst);
   if (!codes || !nibbles || !side || !block_off1 || !block_off2 || !dst) return VCB_ERR_NULL;
   if (n < 0 || n_over < 0) return VCB_ERR_SIZE;
   if (n_over > 0 && (!over_idx || !over_val)) return VCB_ERR_NULL;
@@ -1310,7 +1303,7 @@ int vcb_expand_counts_twolevel(const uint32_t* codes, const uint32_t* nibbles, c
   cudaStream_t st = (cudaStream_t)stream;
   const long long per_block = (long long)VCB_PACKED_BLOCK_WORDS * 16;
   const long long n_blocks = (n + per_block - 1) / per_block;
-  const long long grid = n_blocks < 148LL * 16 ? n_blocks : 148LL * 16;
+  const long long grid = n_blocks < (long long)vcb::sm_count() * 16 ? n_blocks : (long long)vcb::sm_count() * 16;
   vcb::vcb_expand_packed2_kernel<<<(unsigned)grid, VCB_PACKED_BLOCK_WORDS, 0, st>>>(
       codes, nibbles, side, (const long long*)block_off1, (const long long*)block_off2, n, n_blocks, dst);
   cudaError_t e = cudaGetLastError();
@@ -1318,7 +1311,7 @@ int vcb_expand_counts_twolevel(const uint32_t* codes, const uint32_t* nibbles, c
   if (n_over > 0) {
     const int bs = 256;
     long long b = (n_over + bs - 1) / bs;
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > vcb::sm_count() * 8) b = vcb::sm_count() * 8;
     vcb::vcb_scatter_overflow_kernel<<<(unsigned)b, bs, 0, st>>>((const long long*)over_idx, over_val, n_over, dst);
     e = cudaGetLastError();
   }
@@ -1327,6 +1320,7 @@ int vcb_expand_counts_twolevel(const uint32_t* codes, const uint32_t* nibbles, c
 
 int vcb_csr_to_counts(const int64_t* indptr, const int32_t* indices, const void* data, int32_t data_dtype, int64_t Nc,
                       int64_t Ng, int64_t ld, float* dst, int32_t* status, void* stream) {
+  vcb::DeviceGuard guard(dst);
   if (!indptr || !dst) return VCB_ERR_NULL;
   if (Nc < 0 || Ng <= 0 || ld < Ng) return VCB_ERR_SIZE;
   if (ld % 4 != 0 || (((uintptr_t)dst) & 15) != 0) return VCB_ERR_ALIGN;
@@ -1341,7 +1335,7 @@ int vcb_csr_to_counts(const int64_t* indptr, const int32_t* indices, const void*
   if (!indices || !data) return VCB_OK;  // an all-zero matrix (nnz = 0) may come without index / value arrays
   const int bs = 256;
   long long blocks = (Nc + (bs / 32) - 1) / (bs / 32);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > vcb::sm_count() * 16) blocks = vcb::sm_count() * 16;
   const long long* ip = (const long long*)indptr;
   switch (data_dtype) {
     case VCB_CSR_F32: vcb::vcb_csr_to_counts_kernel<float><<<(unsigned)blocks, bs, 0, st>>>(ip, indices, (const float*)data, Nc, Ng, ld, dst, status); break;
@@ -1355,6 +1349,7 @@ int vcb_csr_to_counts(const int64_t* indptr, const int32_t* indices, const void*
 
 int vcb_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_dev,
                      float lr0, float lrd, float beta1, float beta2, float eps, float clip, void* stream) {
+  vcb::DeviceGuard guard(param);
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step_dev) return VCB_ERR_NULL;
   if (n < 0) return VCB_ERR_SIZE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1362,7 +1357,7 @@ int vcb_clipped_adam(float* param, const float* grad, float* exp_avg, float* exp
   if (n > 0) {
     const int bs = 256;
     long long blocks = (n + bs - 1) / bs;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > vcb::sm_count() * 8) blocks = vcb::sm_count() * 8;
     vcb::vcb_clipped_adam_kernel<<<(unsigned)blocks, bs, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n,
                                                                  (const long long*)step_dev, lr0, lrd, beta1, beta2,
                                                                  eps, clip);

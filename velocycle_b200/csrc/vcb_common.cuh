@@ -9,6 +9,32 @@
 
 namespace vcb {
 
+// Host side: run an entry point on the device that OWNS the caller's buffers.  Kernels launch in the calling thread's current
+// device context; a caller that holds tensors on cuda:1 while device 0 is current would otherwise get
+// cudaErrorInvalidResourceHandle (the stream belongs to another device).  The previous device is restored on return.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  explicit DeviceGuard(const void* device_ptr) {
+    cudaPointerAttributes at;
+    if (device_ptr != nullptr && cudaPointerGetAttributes(&at, device_ptr) == cudaSuccess &&
+        (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+      dev = at.device;
+      if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+        cudaSetDevice(dev);
+      } else {
+        prev = -1;
+      }
+    } else {
+      cudaGetLastError();  // a host pointer is an argument error for the entry point to report, not a sticky CUDA error
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr double kLn2d = 0.693147180559945309417232121458;

@@ -26,6 +26,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "vcb_common.cuh"
+
 namespace vcb {
 
 constexpr int kSviThreads = 256;
@@ -325,6 +327,7 @@ int vcb_svi_partials(int64_t Nc, int64_t Ng, int64_t* n_cell_blocks, int64_t* n_
 }
 
 int vcb_svi_sample(const vcb_svi_t* p, void* stream) {
+  vcb::DeviceGuard guard(p ? p->param : nullptr);
   int rc = vcb::svi_validate(p);
   if (rc != VCB_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -341,6 +344,7 @@ int vcb_svi_sample(const vcb_svi_t* p, void* stream) {
 }
 
 int vcb_svi_backward(const vcb_svi_t* p, void* stream) {
+  vcb::DeviceGuard guard(p ? p->param : nullptr);
   int rc = vcb::svi_validate(p);
   if (rc != VCB_OK) return rc;
   if (!p->lp_S || !p->d_nu || !p->d_shape_inv || !p->d_phi) return VCB_ERR_NULL;

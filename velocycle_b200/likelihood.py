@@ -8,7 +8,6 @@ observed value, but its ``log_prob`` is the per-gene sum over cells that the CUD
 """
 from __future__ import annotations
 
-import weakref
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -43,39 +42,55 @@ class without_count_sites:
 def count_sites_enabled() -> bool:
     return _COUNT_SITES
 
-_SIDECARS: Dict[Tuple, PackedCounts] = {}
+_ATTR = "_vcb_packed_counts"  # the sidecar rides on the count TENSOR: it lives and dies with mp.S
+
+
+def _design_key(mp, need_U: bool) -> Tuple:
+    """What the packed counts were derived from besides ``mp.S``: the unspliced matrix and the design tensors (identity and
+    in-place version), so that re-preprocessing the same matrix with another design, or freeing and re-allocating a
+    dataset at the same address, can never hand back stale counts / batch ids."""
+    def ident(t):
+        return None if t is None else (id(t), t.data_ptr(), getattr(t, "_version", 0), tuple(t.shape))
+
+    return (ident(getattr(mp, "U", None)) if need_U else None, ident(getattr(mp, "Db", None)),
+            ident(getattr(mp, "D", None)) if need_U else None)
 
 
 def attach_packed_counts(mp, counts: PackedCounts) -> None:
     """Register ready-made packed counts for ``mp`` (what ``preprocess_for_*`` of this package does)."""
-    _SIDECARS[_key(mp)] = counts
-
-
-def _key(mp) -> Tuple:
-    U = getattr(mp, "U", None)
-    return (mp.S.data_ptr(), tuple(mp.S.shape), 0 if U is None else U.data_ptr(), str(mp.S.device))
+    setattr(mp.S, _ATTR, {True: (_design_key(mp, True), counts), False: (_design_key(mp, False), counts)})
 
 
 def packed_counts_for(mp, need_U: bool) -> PackedCounts:
-    """Packed, device-resident counts for a metaparameter tuple; built once per dataset and cached.
+    """Packed, device-resident counts for a metaparameter tuple; built once per dataset and kept ON ``mp.S`` (an attribute of
+    the tensor object: no global table, nothing outlives the data).
 
     Works for ``mp`` objects made by the reference's own preprocessing: ``mp.S`` / ``mp.U`` logical (Ng,Nc)
     float tensors, one-hot ``mp.Db`` and ``mp.D``."""
     pc = getattr(mp, "packed_counts", None)
     if pc is not None:
         return pc
-    k = _key(mp)
-    pc = _SIDECARS.get(k)
-    if pc is None or (need_U and pc.U is None):
-        if not mp.S.is_cuda:
-            raise _lib.VcbError(
-                "velocycle_b200 models need mp.S / mp.U on a CUDA device: there is no CPU path "
-                "(pass device=torch.device('cuda') to preprocess_for_*_estimation)"
-            )
-        pc = PackedCounts.from_model_tensors(
-            mp.S, mp.U if need_U else None, getattr(mp, "Db", None), getattr(mp, "D", None) if need_U else None
+    cache = getattr(mp.S, _ATTR, None)
+    if cache is None:
+        cache = {}
+        setattr(mp.S, _ATTR, cache)
+    key = _design_key(mp, need_U)
+    hit = cache.get(need_U)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    if not need_U:  # counts packed together with U serve the phase model as well (same S, same batch design)
+        hit = cache.get(True)
+        if hit is not None and hit[0][1] == key[1]:
+            return hit[1]
+    if not mp.S.is_cuda:
+        raise _lib.VcbError(
+            "velocycle_b200 models need mp.S / mp.U on a CUDA device: there is no CPU path "
+            "(pass device=torch.device('cuda') to preprocess_for_*_estimation)"
         )
-        _SIDECARS[k] = pc
+    pc = PackedCounts.from_model_tensors(
+        mp.S, mp.U if need_U else None, getattr(mp, "Db", None), getattr(mp, "D", None) if need_U else None
+    )
+    cache[need_U] = (key, pc)
     return pc
 
 

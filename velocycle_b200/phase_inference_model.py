@@ -63,7 +63,8 @@ def expected_log_counts(mp, nu, phi, dnu=None):
     zeta = torch_fourier_basis(phi.reshape(-1), num_harmonics=(nu.shape[-1] - 1) // 2, der=0)
     out = nu.reshape(mp.Ng, -1) @ zeta.T + mp.count_factor.reshape(1, -1)
     if dnu is not None:
-        bid = packed_counts_for(mp, need_U=False).batch_id.long()
+        pc = packed_counts_for(mp, need_U=False)
+        bid = (pc.batch_id if pc.perm is None else pc.batch_id[pc.inv_perm]).long()  # the caller's cell order
         out = out + dnu.reshape(mp.Nb, mp.Ng)[bid].T
     return out
 
