@@ -74,6 +74,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps of the headline workload (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -313,7 +315,7 @@ class Workload:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def time_steps(self, steps, warmup, fn=None):
+    def time_steps(self, steps, warmup, fn=None, profiler_range=False):
         """ms per step (CUDA events, MAX over ranks) and the streaming kernel's mean event duration on this rank."""
         import torch.distributed as dist
 
@@ -323,12 +325,16 @@ class Workload:
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kern = []
+        if profiler_range:
+            torch.cuda.cudart().cudaProfilerStart()
         e0.record()
         for _ in range(steps):
             fn()  # returns the loss as a Python float: one D2H read + sync per step, as pyro.infer.SVI.step does
             kern.append(self.ev.elapsed_ms())
         e1.record()
         self.barrier()
+        if profiler_range:
+            torch.cuda.cudart().cudaProfilerStop()
         t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -507,7 +513,7 @@ def run_ours(a):
     # ---- the headline workload ---------------------------------------------------------------------------------------
     w = Workload(a, Nc, Ng, dev, rank, world)
     sampler, path = start_clock_sampler(local_rank) if rank == 0 else (None, None)
-    ms_per_step, kern = w.time_steps(a.steps, a.warmup)
+    ms_per_step, kern = w.time_steps(a.steps, a.warmup, profiler_range=a.profiler_range)
     clocks = stop_clock_sampler(sampler, path) if rank == 0 else None
     value = Nc * world * Ng / (ms_per_step * 1e-3)
     roofline = w.roofline(kern)
