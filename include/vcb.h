@@ -254,6 +254,24 @@ int vcb_svi_partials(int64_t Nc, int64_t Ng, int64_t* n_cell_blocks, int64_t* n_
 int vcb_svi_sample(const vcb_svi_t* p, void* stream);
 int vcb_svi_backward(const vcb_svi_t* p, void* stream);
 
+
+/* ---- one-shot SUM all-reduce over NVLink peer memory (csrc/vcb_comm.cu) -----------------------------------------------------
+ * The step's single exchange under cell sharding (north_star: "gene-level parameter gradients are summed with a single
+ * allreduce over NVLink per step").  slots[r] / flags[r] point at rank r's receive buffer (2 x world x slot_floats floats)
+ * and flag words (2 x world uint32, zero-initialised), mapped into this process with CUDA IPC; `epoch` is a uint32 in this
+ * rank's device memory, zero-initialised, advanced by every call.  All ranks must call with the same n (a multiple of 4,
+ * <= slot_floats) in the same order.  The sum is taken in rank order: reproducible and identical on every rank.            */
+#define VCB_MAX_RANKS 16
+typedef struct vcb_comm_t {
+  int32_t rank, world;
+  int64_t slot_floats;
+  float* slots[VCB_MAX_RANKS];
+  uint32_t* flags[VCB_MAX_RANKS];
+  uint32_t* epoch;
+} vcb_comm_t;
+
+int vcb_allreduce_sum(const vcb_comm_t* c, float* data, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

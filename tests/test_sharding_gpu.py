@@ -75,6 +75,57 @@ def _worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
+def _comm_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from velocycle_b200.sharding import PeerComm, ShardInfo
+
+    n = 22_532
+    comm = PeerComm.create(ShardInfo.make(1000), n, dev)
+    assert comm is not None
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    for it in range(7):  # odd and even epochs, both buffer sets reused several times
+        x = torch.randn(n, generator=g, device=dev) * (10.0 ** (it - 3))
+        ref = x.clone()
+        dist.all_reduce(ref)
+        comm.allreduce_(x)
+        assert torch.allclose(x, ref, rtol=1e-6, atol=1e-30), it
+        same = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(same, x)
+        assert all(torch.equal(same[0], t) for t in same), "the one-shot sum must be bitwise identical on every rank"
+    # inside a CUDA graph: replays advance the device-side epoch
+    buf = torch.zeros(n, device=dev)
+    src = torch.full((n,), float(rank + 1), device=dev)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        buf.copy_(src)
+        comm.allreduce_(buf)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        buf.copy_(src)
+        comm.allreduce_(buf)
+    for _ in range(5):
+        graph.replay()
+        torch.cuda.synchronize()
+        assert float(buf[0]) == world * (world + 1) / 2 and float(buf[-1]) == world * (world + 1) / 2
+    open(os.path.join(tmp, f"comm{rank}"), "w").write("ok")
+    dist.barrier()
+    os._exit(0)  # (peer mappings and NCCL communicators: skip the teardown)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_one_shot_peer_allreduce_matches_nccl(tmp_path):
+    world = min(torch.cuda.device_count(), 8)
+    mp.spawn(_comm_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"comm{r}").exists() for r in range(world))
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_sharded_fit_matches_single_gpu(tmp_path):
     world = 2

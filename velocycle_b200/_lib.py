@@ -68,6 +68,16 @@ class VcbSvi(C.Structure):
     )
 
 
+VCB_MAX_RANKS = 16
+
+
+class VcbComm(C.Structure):
+    """``vcb_comm_t`` of include/vcb.h."""
+
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("slot_floats", C.c_int64),
+                ("slots", C.c_void_p * VCB_MAX_RANKS), ("flags", C.c_void_p * VCB_MAX_RANKS), ("epoch", C.c_void_p)]
+
+
 EXPORTS = (
     "vcb_version",
     "vcb_strerror",
@@ -83,6 +93,7 @@ EXPORTS = (
     "vcb_svi_partials",
     "vcb_svi_sample",
     "vcb_svi_backward",
+    "vcb_allreduce_sum",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -141,6 +152,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(VcbSvi), C.c_void_p]
+    lib.vcb_allreduce_sum.restype = C.c_int
+    lib.vcb_allreduce_sum.argtypes = [C.POINTER(VcbComm), C.c_void_p, C.c_int64, C.c_void_p]
     _lib = lib
     return lib
 

@@ -31,9 +31,9 @@ namespace s2 {
 
 constexpr int kGPS = 2;                          // 8-cell groups per ring stage
 constexpr int kStageCells = kGPS * kGroupCells;  // 16
-constexpr int kD = 4;                            // count groups in flight per warp (two stages)
+constexpr int kD = 4;                            // count groups in flight per warp
 constexpr int kMaxNS = 8;                        // table-ring depth limit (mbarrier slots)
-constexpr int kThreads = 512;
+constexpr int kThreads = 512;  // 16 warps x 128 registers: 20-24 warps at 80-96 registers spill and lose 30 % (tried)
 constexpr int kHeader = 256;
 constexpr int kSvcDist = 2;  // a stage is serviced (table slot refilled, parked cell partials drained) this many stages later
 constexpr float kRelEps = 1e-5f;
@@ -472,12 +472,13 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   int p_slot = 0;               // park slot of the current stage
   // one 8-cell group of the current stage: consume, reduce the per-cell sums over the warp's genes, park them, refill the
   // count slot
-  auto do_group = [&](auto masked_tag, const int h, const float* tb_stage, const float4* cnt_stage, float* part_stage, const int d0) {
+  int c_ring = 0;  // count-ring slot of the next group to consume (and, once consumed, to refill)
+  auto do_group = [&](auto masked_tag, const int h, const float* tb_stage, float* part_stage) {
     constexpr bool MASKED = decltype(masked_tag)::value;
     cp_async_wait<D - 1>();
     __syncwarp();
     const float* tb = tb_stage + h * TABG;
-    const float4* cnt = cnt_stage + (size_t)h * NLD * nthr;
+    const float4* cnt = s_cnt + (size_t)c_ring * NLD * nthr;
     float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
     if (MASKED) {
       // mixed stage: one masked pass per batch present among the 16 cells (warp-uniform decisions)
@@ -514,7 +515,8 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       }
     }
     __syncwarp();  // every lane has read its counts: the slot may be refilled
-    load_counts(d0 + h);
+    load_counts(c_ring);
+    c_ring = c_ring + 1 == D ? 0 : c_ring + 1;
   };
   // Leave stage st: the tables of the slot and this warp's parked partials are final (the __syncwarp in do_group orders the
   // other lanes' accesses before lane 0's arrival); then the rotating service duty for the stage that starts next.
@@ -526,13 +528,11 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       c_phase ^= 1;
     }
     const int nx = st + 1;
-    if (nx < n_stages && nx >= kSvcDist && ((nx - warp) & (nwarps - 1)) == 0) service(nx - kSvcDist);
+    if (nx < n_stages && nx >= kSvcDist && (nx - warp) % nwarps == 0) service(nx - kSvcDist);
   };
   for (int st = 0; st < n_stages; ++st) {
     mbar_wait(full0 + 8 * c_slot, (uint32_t)c_phase);
     const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
-    const int d0 = (st & 1) * kGPS;
-    const float4* cnt_stage = s_cnt + (size_t)d0 * NLD * nthr;
     // park address of this lane's cell: [p_slot][warp][quantity][cell][group]
     float* part_stage = s_part + (((size_t)p_slot * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4))) * 2;
     const int stage_b = __float_as_int(tb_stage[TAIL + 16]);  // the stage's batch (0 without batches), -1 if its cells disagree
@@ -543,16 +543,16 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     }
     if (stage_b >= 0) {
 #pragma unroll
-      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, h, tb_stage, cnt_stage, part_stage, d0);
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, h, tb_stage, part_stage);
     } else {
-      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, h, tb_stage, cnt_stage, part_stage, d0);
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, h, tb_stage, part_stage);
     }
     leave_stage(st);
   }
   cp_async_wait<0>();
   // the last stages have no successor stage to be serviced from: same rotation, after the loop
   for (int x = (n_stages >= kSvcDist ? n_stages - kSvcDist : 0); x < n_stages; ++x)
-    if (((x + kSvcDist - warp) & (nwarps - 1)) == 0) service(x);
+    if ((x + kSvcDist - warp + nwarps) % nwarps == 0) service(x);
 
   // ---- flush per-gene partial sums -------------------------------------------------------------------------
   if (GRAD) flush_batch();

@@ -23,7 +23,7 @@ import torch
 from . import _lib
 from .fused import VCB_FLAG_GRAD, VcbProblem, _ptr
 from .likelihood import packed_counts_for
-from .sharding import allreduce_flat_
+from .sharding import PeerComm, allreduce_flat_
 
 __all__ = ["FusedStep"]
 
@@ -165,7 +165,10 @@ class FusedStep:
             q.logbeta, q.gamma, q.nu_omega = self.logbeta.data_ptr(), self.gamma.data_ptr(), self.nu_omega.data_ptr()
         sizes = [("lp_S", Ng), ("lp_U", Ng if velocity else 0), ("d_shape_inv", Ng), ("d_logbeta", Ng if velocity else 0),
                  ("d_gamma", Ng if velocity else 0), ("d_nu", Ng * K), ("d_dnu", Nb * Ng), ("d_nu_omega", Nx * Kw if velocity else 0)]
-        self.gene_flat = torch.zeros(sum(n for _, n in sizes) + 1, dtype=torch.float32, device=dev)
+        n_flat = sum(n for _, n in sizes) + 1
+        self.gene_flat = torch.zeros((n_flat + 3) // 4 * 4, dtype=torch.float32, device=dev)  # (128-bit exchange)
+        # the step's exchange under cell sharding: one kernel over NVLink peer memory, NCCL when the mapping is not possible
+        self.comm = PeerComm.create(self.shard, self.gene_flat.numel(), dev) if self.g.peer_allreduce else None
         off = 0
         base = self.gene_flat.data_ptr()
         for name, n in sizes:
@@ -232,7 +235,10 @@ class FusedStep:
         mark("sample")
         _lib.check(self.like_fn(C.byref(self.q), self.ws.data_ptr(), self.ws_bytes, st), "likelihood")
         mark("likelihood")
-        allreduce_flat_(self.gene_flat, self.shard)
+        if self.comm is not None:
+            self.comm.allreduce_(self.gene_flat)
+        else:
+            allreduce_flat_(self.gene_flat, self.shard)
         mark("allreduce")
         _lib.check(self.lib.vcb_svi_backward(C.byref(self.p), st), "vcb_svi_backward")
         mark("backward")

@@ -79,13 +79,14 @@ def agree_across_ranks(flag: bool, mp) -> bool:
 
 class GraphedSVI:
     def __init__(self, model: Callable, guide: Callable, optim_args: Dict, mp, use_graph: bool = True,
-                 warmup_iters: int = 3, fast: bool = True):
+                 warmup_iters: int = 3, fast: bool = True, peer_allreduce: bool = True):
         """``fast``: use the fused step (``faststep.FusedStep``: a dozen launches) when ``model`` / ``guide`` are the package's
         own unconditioned functions; otherwise -- and always with ``fast=False`` -- the step is traced through the effect
         handlers like ``pyro.infer.SVI`` does."""
         self.model, self.guide, self.mp = model, guide, mp
         self._want_fast = fast
         self._fast = None
+        self.peer_allreduce = peer_allreduce  # fused step under cell sharding: vcb_allreduce_sum instead of NCCL
         self.lr0 = float(optim_args.get("lr", 1e-3))
         self.lrd = float(optim_args.get("lrd", 1.0))
         self.betas = tuple(optim_args.get("betas", (0.9, 0.999)))
