@@ -89,10 +89,16 @@ def _comm_worker(rank, world, port, tmp):
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     for it in range(7):  # odd and even epochs, both buffer sets reused several times
         x = torch.randn(n, generator=g, device=dev) * (10.0 ** (it - 3))
-        ref = x.clone()
-        dist.all_reduce(ref)
+        parts = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(parts, x)  # (through NCCL: the independent path)
+        exact = torch.stack(parts).double().sum(0)
+        scale = torch.stack(parts).double().abs().sum(0)
         comm.allreduce_(x)
-        assert torch.allclose(x, ref, rtol=1e-6, atol=1e-30), it
+        assert bool(((x.double() - exact).abs() <= 1e-6 * scale + 1e-30).all()), it
+        seq = parts[0].clone()
+        for t in parts[1:]:
+            seq += t
+        assert torch.equal(x, seq), "the sum is taken in rank order 0..world-1"
         same = [torch.empty_like(x) for _ in range(world)]
         dist.all_gather(same, x)
         assert all(torch.equal(same[0], t) for t in same), "the one-shot sum must be bitwise identical on every rank"
