@@ -36,7 +36,17 @@ struct CellParams {
   int H, Hw, Nx, velo, tabg;
   int v2;  // tables for vcb_stream2.cuh: omega * ln2 in the tail, backward sections as {Zhi, Zhi, Zlo, Zlo} TF32 pairs,
            // slot 16 of the first group of every 16-cell stage = the stage's batch (or -1)
+  // The first n_spec_blocks blocks evaluate the parameter-only lgamma / digamma sums over the count spectra (fp64, the slow
+  // part of the per-gene epilogue).  They depend on shape_inv alone, so they run here, beside the table blocks and before
+  // the streaming kernel, instead of on the serial tail of the step; spec_out = [Ng][4] doubles {lgS, psS, lgU, psU}.
+  unsigned n_spec_blocks;
+  vcb_spectrum_t spec_S, spec_U;
+  const float* shape_inv;
+  double* spec_out;
+  long long Ng;
 };
+
+__device__ void spectrum_block(const CellParams& P, unsigned block);
 
 constexpr int kCellEpiThreads = 256;
 constexpr int kTabWarps = 8;
@@ -46,8 +56,12 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
   // per warp and cell: [0] forward eta operand, [1] zeta', [2] omega*zeta'', [3] backward zeta, [4] omega*zeta'
   __shared__ float sv[kTabWarps][5][kGroupCells][kTabSlots];
   __shared__ float s_tail[kTabWarps][20];
+  if (blockIdx.x < P.n_spec_blocks) {  // the first blocks: they are the long ones (fp64 lgamma / digamma), start them first
+    spectrum_block(P, blockIdx.x);
+    return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long group = (long long)blockIdx.x * kTabWarps + warp;
+  const long long group = (long long)(blockIdx.x - P.n_spec_blocks) * kTabWarps + warp;
   if (group >= P.n_groups) return;
   const int H = P.H, K = 2 * H + 1, KS = ksteps(H);
   if (lane < kGroupCells) {
@@ -253,6 +267,7 @@ struct GeneEpiParams {
   int dnu_rows;  // single batch, d/ddnu = the constant column of d/dnu (tcgen05 path): no atomics buffer
   int v2;        // partial rows written by vcb_stream2: ROW_AS / ROW_AU already hold the -r L terms, ROW_LS = sum(LS + LU);
                  // dnu_acc = per-split batch sums [n_split][Nb][ld] (the constant column of ROW_DNU is then zero)
+  const double* spec_pre;  // [Ng][4] spectrum sums evaluated beside the table kernel (see CellParams), or null: evaluate here
 };
 
 constexpr int kEpiGenes = 8;
@@ -271,6 +286,30 @@ __device__ __forceinline__ void spectrum_sums(const vcb_spectrum_t& sp, long lon
     const double k = (double)sp.val[e], m = (double)sp.mult[e];
     lg_sum += m * (lgamma(r + k) - lgr);
     psi_sum += m * (digamma_d(r + k) - psr);
+  }
+}
+
+// the spectrum role of the table kernel's extra blocks: block b serves genes [8 b, 8 b + 8), 32 lanes per gene
+__device__ void spectrum_block(const CellParams& P, unsigned block) {
+  __shared__ double s_sp[4][kEpiLanes][kEpiGenes];
+  const int gx = threadIdx.x % kEpiGenes, ly = threadIdx.x / kEpiGenes;
+  const long long g = (long long)block * kEpiGenes + gx;
+  const bool valid = g < P.Ng;
+  double a = 0, b = 0, c = 0, d = 0;
+  if (valid) {
+    const double r = 1.0 / (double)P.shape_inv[g];
+    spectrum_sums(P.spec_S, g, r, ly, kEpiLanes, a, b);
+    if (P.spec_U.off != nullptr) spectrum_sums(P.spec_U, g, r, ly, kEpiLanes, c, d);
+  }
+  s_sp[0][ly][gx] = a;
+  s_sp[1][ly][gx] = b;
+  s_sp[2][ly][gx] = c;
+  s_sp[3][ly][gx] = d;
+  __syncthreads();
+  if (ly < 4 && valid) {  // fixed summation order: deterministic
+    double t = 0.0;
+    for (int l = 0; l < kEpiLanes; ++l) t += s_sp[ly][l][gx];
+    P.spec_out[g * 4 + ly] = t;
   }
 }
 
@@ -326,8 +365,17 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
   {
     double a = 0, b = 0, c = 0, d = 0;
     if (valid && !P.lginline) {
-      spectrum_sums(P.spec_S, g, r, ly, kEpiLanes, a, b);
-      if (P.velo) spectrum_sums(P.spec_U, g, r, ly, kEpiLanes, c, d);
+      if (P.spec_pre != nullptr) {
+        if (ly == 0) {
+          a = P.spec_pre[g * 4 + 0];
+          b = P.spec_pre[g * 4 + 1];
+          c = P.spec_pre[g * 4 + 2];
+          d = P.spec_pre[g * 4 + 3];
+        }
+      } else {
+        spectrum_sums(P.spec_S, g, r, ly, kEpiLanes, a, b);
+        if (P.velo) spectrum_sums(P.spec_U, g, r, ly, kEpiLanes, c, d);
+      }
     }
     s_spec[0][ly][gx] = a;
     s_spec[1][ly][gx] = b;
@@ -729,7 +777,7 @@ static Plan make_plan(const vcb_problem_t* p, bool velo) {
 struct Plan2 {
   int n_tiles, n_split, n_ring, tabg, rows, NQ, smem, n_cell_blocks;
   long long n_stages, n_groups, Ncp;
-  size_t off_tab, off_genepart, off_cellpart, off_dnupart, off_dnwpart, total;
+  size_t off_tab, off_genepart, off_cellpart, off_dnupart, off_dnwpart, off_spec, total;
 };
 
 static bool stream2_applies(const vcb_problem_t* p) {
@@ -770,6 +818,8 @@ static Plan2 make_plan2(const vcb_problem_t* p, bool velo) {
   pl.off_dnwpart = off;
   pl.n_cell_blocks = (int)((p->Nc + kCellEpiThreads - 1) / kCellEpiThreads);
   off = align_up(off + (size_t)(pl.n_cell_blocks > 0 ? pl.n_cell_blocks : 1) * (p->Nx > 0 ? p->Nx : 1) * (2 * p->Hw + 1) * 8, 256);
+  pl.off_spec = off;
+  off = align_up(off + (size_t)p->Ng * 4 * 8, 256);
   pl.total = off;
   return pl;
 }
@@ -1005,6 +1055,7 @@ static int run2(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_by
   float* cellpart = (float*)(ws + pl.off_cellpart);
   float* dnupart = (grad && p->Nb > 0) ? (float*)(ws + pl.off_dnupart) : nullptr;
   double* dnw_part = (double*)(ws + pl.off_dnwpart);
+  double* spec_pre = (double*)(ws + pl.off_spec);
   cudaError_t e;
   if (dnupart) {
     e = cudaMemsetAsync(dnupart, 0, (size_t)pl.n_split * p->Nb * p->ld * 4, st);
@@ -1013,7 +1064,15 @@ static int run2(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_by
   {
     CellParams cp{p->phi, p->cf, p->Nb > 0 ? p->batch_id : nullptr, p->cond_id, velo ? p->nu_omega : nullptr,
                   tab,    p->Nc, pl.n_groups, p->H, p->Hw, p->Nx, velo ? 1 : 0, pl.tabg, 1};
-    vcb_cell_tables_kernel<<<(unsigned)((pl.n_groups + kTabWarps - 1) / kTabWarps), kTabWarps * 32, 0, st>>>(cp);
+    const unsigned n_table_blocks = (unsigned)((pl.n_groups + kTabWarps - 1) / kTabWarps);
+    const unsigned n_spec_blocks = (unsigned)((p->Ng + kEpiGenes - 1) / kEpiGenes);
+    cp.n_spec_blocks = n_spec_blocks;
+    cp.spec_S = p->spec_S;
+    if (velo) cp.spec_U = p->spec_U;
+    cp.shape_inv = p->shape_inv;
+    cp.spec_out = spec_pre;
+    cp.Ng = p->Ng;
+    vcb_cell_tables_kernel<<<n_table_blocks + n_spec_blocks, kTabWarps * 32, 0, st>>>(cp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
@@ -1066,6 +1125,7 @@ static int run2(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_by
     ge.grad = grad;
     ge.lginline = 0;
     ge.v2 = 1;
+    ge.spec_pre = spec_pre;
     vcb_gene_epilogue_kernel<<<(unsigned)((p->Ng + kEpiGenes - 1) / kEpiGenes), kEpiGenes * kEpiLanes, 0, st>>>(ge);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
