@@ -281,11 +281,14 @@ __device__ __forceinline__ void spectrum_sums(const vcb_spectrum_t& sp, long lon
   if (sp.off == nullptr) return;
   const int e0 = sp.off[g], e1 = sp.off[g + 1];
   if (e1 <= e0) return;
-  const double lgr = lgamma(r), psr = digamma_d(r);
+  double lgr, psr;
+  lgamma_digamma_d(r, lgr, psr);
   for (int e = e0 + lane; e < e1; e += nlanes) {
     const double k = (double)sp.val[e], m = (double)sp.mult[e];
-    lg_sum += m * (lgamma(r + k) - lgr);
-    psi_sum += m * (digamma_d(r + k) - psr);
+    double lgk, psk;
+    lgamma_digamma_d(r + k, lgk, psk);
+    lg_sum += m * (lgk - lgr);
+    psi_sum += m * (psk - psr);
   }
 }
 
