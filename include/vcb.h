@@ -239,6 +239,10 @@ typedef struct vcb_svi_t {
   const float* phixy_prior;                  /* [Nc][2] */
   const int64_t* cell_row;                   /* [Nc] or NULL: row of cell c in the (batch-sorted) count matrices; phi and d_phi
                                                 are indexed by row, everything else here by cell */
+  /* conditioned sites (poutine.condition on the model + poutine.block on the guide, the tutorial's velocity stage,
+     phase_inference_model.py:110-115): the site takes the given value, keeps its prior log-prob, loses its guide term and
+     its parameters get a zero gradient; NULL = sampled from the guide.  (The draws are made all the same: RNG parity.) */
+  const float *cond_nu, *cond_dnu, *cond_shape_inv, *cond_phixy; /* [Ng][K], [Nb][Ng], [Ng], [Nc][2] */
   float sd_dnu, gamma_alpha, gamma_beta, rho_mean, rho_std, rho_scale;
   /* sampled values: written by vcb_svi_sample, inputs of the likelihood call and of vcb_svi_backward */
   float *nu, *dnu, *shape_inv, *loggamma, *gamma, *logbeta, *nu_omega, *phixy, *phi;

@@ -29,8 +29,8 @@ def test_problem_struct_matches_header_layout():
     # 3 int64 + 6 int32/uint32 + 12 pointers + 2*4 spectrum pointers + 11 output pointers + 2 event handles
     assert C.sizeof(_lib.VcbProblem) == 3 * 8 + 6 * 4 + 12 * 8 + 8 * 8 + 11 * 8 + 2 * 8
     assert C.sizeof(_lib.VcbSpectrum) == 32
-    # vcb_svi_t: 2 int64 + 6 int32 + 2 pointers + 15 int64 offsets + 17 pointers + 6 floats + 23 pointers
-    assert C.sizeof(_lib.VcbSvi) == 2 * 8 + 6 * 4 + 2 * 8 + 15 * 8 + 17 * 8 + 6 * 4 + 23 * 8
+    # vcb_svi_t: 2 int64 + 6 int32 + 2 pointers + 15 int64 offsets + 21 pointers + 6 floats + 23 pointers
+    assert C.sizeof(_lib.VcbSvi) == 2 * 8 + 6 * 4 + 2 * 8 + 15 * 8 + 21 * 8 + 6 * 4 + 23 * 8
 
 
 def test_argument_validation_needs_no_gpu():

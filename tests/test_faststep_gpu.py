@@ -64,17 +64,63 @@ def test_trajectory_matches_traced_step(kind, use_graph):
     assert float((pf[finite] - pt[finite]).abs().max()) <= 5e-3
 
 
-def test_conditioned_model_falls_back_to_the_traced_step():
+def _conditioned(kind, sites, fast, use_graph, steps, seed=77):
+    from test_golden_cpu import section
     from velocycle_b200 import ppl as pyro
     from velocycle_b200.ppl import poutine
     from velocycle_b200.svi import GraphedSVI
 
     z, inp = load("case_stereo")
-    mp = _mp(inp, "phase")
+    mp = _mp(inp, kind)
+    draws = section(z, kind, "draw")
+    cond = {k: draws[k].cuda() for k in sites}
+    pyro.clear_param_store()
+    pyro.set_rng_seed(seed)
+    g = GraphedSVI(poutine.condition(mp.model_fn, data=cond), poutine.block(mp.guide_fn, hide=list(cond)), dict(ARGS), mp,
+                   use_graph=use_graph, fast=fast)
+    losses = np.array([g.step() for _ in range(steps)])
+    return g, losses
+
+
+@pytest.mark.parametrize("kind,sites", [("velocity_lrmn", ("ϕxy", "ν", "shape_inv", "Δν")), ("velocity", ("ϕxy", "ν")),
+                                        ("phase", ("shape_inv",)), ("velocity_lrmn", ("Δν",))])
+def test_conditioned_fit_uses_the_fused_step_and_matches_the_traced_one(kind, sites):
+    """The tutorial pattern (condition the velocity model on the phase stage's ϕxy, ν, shape_inv, Δν; block them in the
+    guide) and subsets of it: conditioned sites take the given values, keep their prior term, lose the guide term, their
+    parameters do not move; the draws are consumed all the same.  Loss 1e-5, gradients 1e-3 (velocity: the relu kink),
+    8-step trajectory 5e-3."""
+    gt, lt = _conditioned(kind, sites, fast=False, use_graph=False, steps=1)
+    grads_t = {n: gt.flat_grad[o: o + sz].clone() for n, (o, sz) in gt.param_slices.items()}
+    gf, lf = _conditioned(kind, sites, fast=True, use_graph=False, steps=1)
+    assert gf._fast is not None and gf._fast.conditioned == sorted(sites) and gt._fast is None
+    assert abs(lf[0] - lt[0]) <= 1e-5 * abs(lt[0]), (lf, lt)
+    for n, (o, sz) in gf.param_slices.items():
+        got, ref = gf.flat_grad[o: o + sz].double(), grads_t[n].double()
+        err = float((got - ref).abs().max() / (ref.abs().max() + 1e-30))
+        assert err <= (1e-4 if kind == "phase" else 1e-3), (n, err)
+    gt, lt = _conditioned(kind, sites, fast=False, use_graph=False, steps=8)
+    pt = gt.flat_param.clone()
+    gf, lf = _conditioned(kind, sites, fast=True, use_graph=True, steps=8)
+    assert np.all(np.abs(lf - lt) <= 1e-5 * np.abs(lt)), (lf, lt)
+    finite = torch.isfinite(pt)
+    assert float((gf.flat_param[finite] - pt[finite]).abs().max()) <= 5e-3
+    if "ϕxy" in sites:  # conditioned sites receive no updates
+        o, sz = gf.param_slices["ϕxy_locs"]
+        z, inp = load("case_stereo")
+        assert torch.equal(gf.flat_param[o: o + sz].cpu().reshape(-1, 2), inp["phixy_prior"].float())
+
+
+def test_other_conditioning_falls_back_to_the_traced_step():
+    from velocycle_b200 import ppl as pyro
+    from velocycle_b200.ppl import poutine
+    from velocycle_b200.svi import GraphedSVI
+
+    z, inp = load("case_stereo")
+    mp = _mp(inp, "velocity")
     pyro.clear_param_store()
     pyro.set_rng_seed(1)
-    cond = {"shape_inv": torch.full((mp.Ng, 1), 0.5, device="cuda")}
-    g = GraphedSVI(poutine.condition(mp.model_fn, data=cond), poutine.block(mp.guide_fn, hide=["shape_inv"]), dict(ARGS), mp,
+    cond = {"logβg": torch.full((mp.Ng, 1), 2.0, device="cuda")}
+    g = GraphedSVI(poutine.condition(mp.model_fn, data=cond), poutine.block(mp.guide_fn, hide=["logβg"]), dict(ARGS), mp,
                    use_graph=False)
     assert np.isfinite(g.step()) and g._fast is None
 

@@ -102,10 +102,10 @@ def test_conditioned_velocity_fit_driver_runs_and_matches():
     fit.fit(ClippedAdam({"lr": 0.03, "betas": (0.8, 0.99)}), num_steps=15, verbose=False)
     assert len(fit.losses) == 15 and np.isfinite(fit.losses).all()
     assert fit.losses[-1] < fit.losses[0]
-    # the driver ran the captured-graph step (traced once: the conditioned sites are constants inside the graph), not the
-    # fused step, which only serves the unconditioned pairs
+    # the driver ran the graphed, fused step with the four sites held at the given values
     g = next(iter(fit._steppers.values()))[0]
-    assert g._graph is not None and g._fast is None and g.steps_done == 15
+    assert g._graph is not None and g.steps_done == 15
+    assert g._fast is not None and g._fast.conditioned == sorted(cond)
     assert fit.posterior["νω"].shape[0] == 4 and fit.posterior["ω"].shape[-1] == mp.Nc
     # conditioned sites receive no updates
     assert torch.equal(pyro.param("ϕxy_locs").detach().cpu(), inp["phixy_prior"].float())

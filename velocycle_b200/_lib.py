@@ -60,7 +60,8 @@ class VcbSvi(C.Structure):
                                     "o_nuw_locs", "o_nuw_scales", "o_loc", "o_cov_factor", "o_cov_diag", "o_rho_real_loc")]
         + [(n, C.c_void_p) for n in ("eps_nu", "eps_loggamma", "eps_logbeta", "eps_nuw", "eps_phixy", "eps_W", "eps_D",
                                      "mu_nu", "sd_nu", "mu_loggamma", "sd_loggamma", "mu_logbeta", "sd_logbeta",
-                                     "mu_nuw", "sd_nuw", "phixy_prior", "cell_row")]
+                                     "mu_nuw", "sd_nuw", "phixy_prior", "cell_row",
+                                     "cond_nu", "cond_dnu", "cond_shape_inv", "cond_phixy")]
         + [(n, C.c_float) for n in ("sd_dnu", "gamma_alpha", "gamma_beta", "rho_mean", "rho_std", "rho_scale")]
         + [(n, C.c_void_p) for n in ("nu", "dnu", "shape_inv", "loggamma", "gamma", "logbeta", "nu_omega", "phixy", "phi",
                                      "lp_S", "lp_U", "d_nu", "d_dnu", "d_shape_inv", "d_logbeta", "d_gamma", "d_nu_omega",

@@ -60,12 +60,19 @@ __global__ void __launch_bounds__(kSviThreads) vcb_svi_cell_sample_kernel(const 
     const float2 loc = reinterpret_cast<const float2*>(P.param + P.o_phixy_locs)[c];
     const float2 e = reinterpret_cast<const float2*>(P.eps_phixy)[c];
     const float2 pr = reinterpret_cast<const float2*>(P.phixy_prior)[c];
-    const float x = loc.x + e.x, y = loc.y + e.y;  // Normal(locs, 1).rsample()
+    float x = loc.x + e.x, y = loc.y + e.y;  // Normal(locs, 1).rsample()
+    if (P.cond_phixy != nullptr) {
+      const float2 v = reinterpret_cast<const float2*>(P.cond_phixy)[c];
+      x = v.x;
+      y = v.y;
+    }
     reinterpret_cast<float2*>(P.phixy)[c] = make_float2(x, y);
     P.phi[P.cell_row ? P.cell_row[c] : c] = atan2f(y, x);  // pack_direction, utils.py:488-506
     const double dx = (double)x - pr.x, dy = (double)y - pr.y;
-    // log p - log q: Normal(prior, 1) against Normal(locs, 1) at locs + eps; the 2 x 1/2 log 2pi cancel
-    lp = -0.5 * (dx * dx + dy * dy) + 0.5 * ((double)e.x * e.x + (double)e.y * e.y);
+    // log p - log q: Normal(prior, 1) against Normal(locs, 1) at locs + eps; the 2 x 1/2 log 2pi cancel.  Conditioned: the
+    // prior term alone, constants included
+    lp = P.cond_phixy != nullptr ? -0.5 * (dx * dx + dy * dy) - 2.0 * kHalfLog2Pi
+                                 : -0.5 * (dx * dx + dy * dy) + 0.5 * ((double)e.x * e.x + (double)e.y * e.y);
   }
   const double t = block_sum(lp);
   if (threadIdx.x == 0) P.cell_partials[blockIdx.x] = t;
@@ -81,7 +88,7 @@ __global__ void __launch_bounds__(kSviThreads) vcb_svi_cell_backward_kernel(cons
   // phi = atan2(y, x): dphi/dx = -y / r2, dphi/dy = x / r2; the guide's log q does not depend on locs (pathwise)
   const float ex = dphi * (-z.y / r2) - (z.x - pr.x);
   const float ey = dphi * (z.x / r2) - (z.y - pr.y);
-  reinterpret_cast<float2*>(P.grad + P.o_phixy_locs)[c] = make_float2(-ex, -ey);
+  reinterpret_cast<float2*>(P.grad + P.o_phixy_locs)[c] = P.cond_phixy != nullptr ? make_float2(0.f, 0.f) : make_float2(-ex, -ey);
 }
 
 // ---- genes ---------------------------------------------------------------------------------------------------------
@@ -95,18 +102,21 @@ __global__ void __launch_bounds__(kSviThreads) vcb_svi_gene_sample_kernel(const 
     for (int k = 0; k < K; ++k) {
       const long long i = g * K + k;
       const float s = expf(P.param[P.o_nu_scales + i]), e = P.eps_nu[i];
-      const float v = fmaf(s, e, P.param[P.o_nu_locs + i]);
+      const float v = P.cond_nu != nullptr ? P.cond_nu[i] : fmaf(s, e, P.param[P.o_nu_locs + i]);
       P.nu[i] = v;
-      lp += normal_lp(v, P.mu_nu[i], P.sd_nu[i]) - (-0.5 * (double)e * e - log((double)s) - kHalfLog2Pi);
+      lp += normal_lp(v, P.mu_nu[i], P.sd_nu[i]);
+      if (P.cond_nu == nullptr) lp -= -0.5 * (double)e * e - log((double)s) - kHalfLog2Pi;
     }
     if (P.o_dnu_locs >= 0)
       for (int b = 0; b < P.Nb; ++b) {
-        const float v = P.param[P.o_dnu_locs + (long long)b * Ng + g];  // Delta guide
-        P.dnu[(long long)b * Ng + g] = v;
+        const long long i = (long long)b * Ng + g;
+        const float v = P.cond_dnu != nullptr ? P.cond_dnu[i] : P.param[P.o_dnu_locs + i];  // Delta guide
+        P.dnu[i] = v;
         lp += normal_lp(v, 0.f, P.sd_dnu);
       }
     {
-      const float x = expf(P.param[P.o_shape_inv_locs + g]);  // Delta guide, positive parameter
+      const float x = P.cond_shape_inv != nullptr ? P.cond_shape_inv[g]
+                                                  : expf(P.param[P.o_shape_inv_locs + g]);  // Delta guide, positive parameter
       P.shape_inv[g] = x;
       const double a = P.gamma_alpha, b = P.gamma_beta;
       lp += a * log(b) + (a - 1.0) * log((double)x) - b * (double)x - lgamma(a);
@@ -193,17 +203,19 @@ __global__ void __launch_bounds__(kSviThreads) vcb_svi_gene_backward_kernel(cons
       const float s = expf(P.param[P.o_nu_scales + i]), e = P.eps_nu[i];
       const float sd = P.sd_nu[i];
       const float A = P.d_nu[i] - (P.nu[i] - P.mu_nu[i]) / (sd * sd);  // d ELBO / d nu
-      P.grad[P.o_nu_locs + i] = -A;
-      P.grad[P.o_nu_scales + i] = -(A * e * s + 1.f);  // + log s from the entropy; d/du = d/ds * s
+      const bool c = P.cond_nu != nullptr;                             // conditioned: the guide's parameters see nothing
+      P.grad[P.o_nu_locs + i] = c ? 0.f : -A;
+      P.grad[P.o_nu_scales + i] = c ? 0.f : -(A * e * s + 1.f);  // + log s from the entropy; d/du = d/ds * s
     }
     if (P.o_dnu_locs >= 0)
       for (int b = 0; b < P.Nb; ++b) {
         const long long i = (long long)b * Ng + g;
-        P.grad[P.o_dnu_locs + i] = -(P.d_dnu[i] - P.dnu[i] / (P.sd_dnu * P.sd_dnu));
+        P.grad[P.o_dnu_locs + i] = P.cond_dnu != nullptr ? 0.f : -(P.d_dnu[i] - P.dnu[i] / (P.sd_dnu * P.sd_dnu));
       }
     {
       const float x = P.shape_inv[g];
-      P.grad[P.o_shape_inv_locs + g] = -(P.d_shape_inv[g] + (P.gamma_alpha - 1.f) / x - P.gamma_beta) * x;
+      P.grad[P.o_shape_inv_locs + g] =
+          P.cond_shape_inv != nullptr ? 0.f : -(P.d_shape_inv[g] + (P.gamma_alpha - 1.f) / x - P.gamma_beta) * x;
     }
     if (P.model == 1) {
       const float sg = expf(P.param[P.o_loggamma_scales + g]), eg = P.eps_loggamma[g];

@@ -41,24 +41,38 @@ _FIELD = {"ν_locs": "o_nu_locs", "ν_scales": "o_nu_scales", "Δν_locs": "o_dn
           "rho_real_loc": "o_rho_real_loc"}
 
 
-def model_code(model, guide, mp) -> Optional[int]:
-    """0 / 1 / 2 when (model, guide) is one of the package's standard pairs (see include/vcb.h, vcb_svi_t.model)."""
+_CONDITIONABLE = {"ν": "cond_nu", "Δν": "cond_dnu", "shape_inv": "cond_shape_inv", "ϕxy": "cond_phixy"}
+
+
+def model_code(model, guide, mp):
+    """``(code, conditioned)`` when (model, guide) is one of the package's standard pairs -- code 0 / 1 / 2 as in
+    include/vcb.h (vcb_svi_t.model) -- possibly wrapped the way the fit drivers wrap them for ``condition_on``
+    (``poutine.condition(model, data)`` + ``poutine.block(guide, hide=the same sites)``, phase_inference_model.py:110-115) with
+    sites among ν, Δν, shape_inv, ϕxy (the tutorial's velocity stage conditions on exactly these); otherwise None."""
     from . import phase_inference_guide as pg, phase_inference_model as pm
     from . import velocity_inference_guide as vg, velocity_inference_model as vm
+    from .ppl import poutine as shim_poutine
 
     if getattr(mp, "noisemodel", None) != "NegativeBinomial":
         return None
+    cond = {}
+    if isinstance(model, shim_poutine.ConditionMessenger) and isinstance(guide, shim_poutine.BlockMessenger):
+        if not guide.plain_hide or guide.hide != frozenset(model.data) or not set(model.data) <= set(_CONDITIONABLE):
+            return None
+        cond, model, guide = dict(model.data), model.fn, guide.fn
+        if "Δν" in cond and not mp.with_delta_nu:
+            return None
     if model is pm.phase_latent_variable_model and guide is pg.phase_latent_variable_guide:
-        return 0
+        return 0, cond
     if model is vm.velocity_latent_variable_model and guide is vg.velocity_latent_variable_guide:
-        return 1
+        return 1, cond
     if model is vm.velocity_latent_variable_model_LRMN and guide is vg.velocity_latent_variable_guide_LRMN:
-        return 2
+        return 2, cond
     return None
 
 
 class FusedStep:
-    def __init__(self, gsvi, code: int):
+    def __init__(self, gsvi, code: int, conditioned=None):
         mp = gsvi.mp
         self.g, self.mp, self.code = gsvi, mp, code
         self.lib = _lib.load()
@@ -126,6 +140,14 @@ class FusedStep:
         p.gene_partials = self.partials.data_ptr() + 8 * ncb.value
         p.lik_partials = self.partials.data_ptr() + 8 * (ncb.value + ngb.value)
         p.loss = gsvi.loss_buf.data_ptr()
+        # conditioned sites: fixed values in the layouts the kernels index ([Ng][K], [Nb][Ng], [Ng], [Nc][2])
+        shapes = {"ν": (Ng * K,), "Δν": (max(Nb, 1) * Ng,), "shape_inv": (Ng,), "ϕxy": (2 * Nc,)}
+        for site, value in (conditioned or {}).items():
+            v = torch.as_tensor(value)
+            if v.numel() != shapes[site][0]:
+                raise _lib.VcbError(f"conditioned site {site!r} has {v.numel()} values, expected {shapes[site][0]}")
+            setattr(p, _CONDITIONABLE[site], buf(v.reshape(-1)))
+        self.conditioned = sorted(conditioned or ())
         self.p, self._keep = p, keep
         self.K, self.Nb, self.Nx, self.Kw, self.Nc, self.Ng = K, Nb, Nx, Kw, Nc, Ng
         self._prepare_likelihood()

@@ -200,6 +200,10 @@ class BlockMessenger(Messenger):
     def __init__(self, fn=None, hide_fn=None, expose_fn=None, hide_all=True, hide: Optional[Iterable[str]] = None,
                  expose: Optional[Iterable[str]] = None, hide_types=None, expose_types=None):
         super().__init__(fn)
+        hide = None if hide is None else list(hide)
+        self.hide = None if hide is None else frozenset(hide)  # (read by the fused step to recognise block(guide, hide=sites))
+        self.plain_hide = hide is not None and hide_fn is None and expose_fn is None and expose is None and not hide_types \
+            and not expose_types
         if hide_fn is not None:
             self.hide_fn = hide_fn
         elif expose_fn is not None:

@@ -195,9 +195,9 @@ class GraphedSVI:
         if self._want_fast:
             from .faststep import FusedStep, model_code
 
-            code = model_code(self.model, self.guide, self.mp)
-            if code is not None:
-                self._fast = FusedStep(self, code)
+            found = model_code(self.model, self.guide, self.mp)
+            if found is not None:
+                self._fast = FusedStep(self, found[0], found[1])
         self._validation_prev = primitives.validation_enabled()
         if not self._use_graph:
             self._built = True
