@@ -379,6 +379,42 @@ class Workload:
         acc["stream_kernel"] = self.ev.elapsed_ms()
         return acc
 
+    def posterior_seconds(self, num_samples=100, n_per_bin=50):
+        """Wall time of the posterior extraction the fit drivers do after the loop (velocity_inference_model.py:201-224):
+        ``num_samples`` guide draws replayed through the model in bins of ``n_per_bin``, the reference's return sites, moved
+        to the CPU.  The count sites are skipped (nobody asks for them), so no count byte is streamed."""
+        rs = self.driver._return_sites() if self.model == "velocity" else ["ν", "ϕxy", "ϕ", "ζ", "shape_inv"]
+        self.driver.sample_posterior(num_samples=2, rs=rs)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nbytes = 0
+        for _ in range(max(1, num_samples // n_per_bin)):
+            out = self.driver.sample_posterior(num_samples=n_per_bin, rs=rs)
+            nbytes += sum(v.numel() * v.element_size() for v in out.values())
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, nbytes
+
+    def posterior_device_seconds(self, num_samples=500, n_per_bin=50):
+        """The same extraction kept on the device (``fastposterior.batched_posterior``; what the driver computes before its
+        ``.cpu()``): seconds for ``num_samples`` draws of the reference's return sites."""
+        from velocycle_b200.faststep import model_code
+        from velocycle_b200.fastposterior import batched_posterior
+
+        found = model_code(self.driver.model, self.driver.guide, self.mp)
+        if found is None:
+            return None
+        rs = self.driver._return_sites() if self.model == "velocity" else ["ν", "ϕxy", "ϕ", "ζ", "shape_inv"]
+        batched_posterior(self.mp, found[0], found[1], 2, rs, counts=self.counts)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        nbytes = 0
+        for _ in range(max(1, num_samples // n_per_bin)):
+            out = batched_posterior(self.mp, found[0], found[1], n_per_bin, rs, counts=self.counts)
+            nbytes += sum(v.numel() * v.element_size() for v in out.values())
+            del out
+        torch.cuda.synchronize()
+        return {"seconds": time.perf_counter() - t0, "draws": num_samples, "bytes_produced": nbytes, "count_bytes_streamed": 0}
+
     def close(self):
         from velocycle_b200 import ppl as pyro
 
@@ -386,6 +422,35 @@ class Workload:
         self.gsvi = self.step = self.driver = self.mp = self.counts = None
         pyro.clear_param_store()
         torch.cuda.empty_cache()
+
+
+def conditioned_step_ms(a, w, dev, steps=20):
+    """ms per step of the velocity fit conditioned the way the tutorials condition it (sites phixy, nu, shape_inv, Delta-nu
+    at fixed values, hidden from the guide) on the data of workload ``w``: the fused step with four sites held."""
+    from velocycle_b200 import ppl as pyro
+    from velocycle_b200.ppl.optim import ClippedAdam
+    from velocycle_b200.svi import stepper_for
+    from velocycle_b200.velocity_inference_model import VelocityFitModel
+
+    mp = w.mp
+    cond = {"ϕxy": mp.φxy_prior.detach().clone(), "ν": mp.μνg.detach().clone(),
+            "shape_inv": torch.full((mp.Ng, 1), 0.5, device=dev), "Δν": torch.zeros((mp.Nb, 1, 1, mp.Ng, 1), device=dev)}
+    driver = VelocityFitModel(mp, condition_on=cond, get_posterior=False)
+    pyro.clear_param_store()
+    pyro.set_rng_seed(0)
+    step = stepper_for(driver, driver.model, driver.guide, ClippedAdam(dict(OPT_ARGS)), None, mp)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    fast = getattr(step.__self__, "_fast", None) is not None
+    driver._steppers = {}
+    return {"ms_per_step": e0.elapsed_time(e1) / steps, "fused_step": fast}
 
 
 def shard_parity(dev, rank, world):
@@ -528,6 +593,12 @@ def run_ours(a):
         except Exception as exc:  # pragma: no cover
             e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
     fast = getattr(w.gsvi, "_fast", None) is not None
+    posterior = None
+    if world == 1:
+        try:
+            posterior = w.posterior_device_seconds(500, 50)
+        except Exception as exc:  # pragma: no cover
+            posterior = {"error": repr(exc)}
     w.close()
 
     # ---- N > 1: the weak-scaling figure next to the strong one ---------------------------------------------------------
@@ -560,6 +631,12 @@ def run_ours(a):
                                  "ms_per_step": ms_c, "svi_steps_per_sec": 1e3 / ms_c,
                                  "value": kw["Nc"] * kw["Ng"] / (ms_c * 1e-3), "unit": UNIT, "kernel_ms": kern_c,
                                  "roofline_frac": rl["frac"], "roofline": rl, "breakdown_ms": c.breakdown()}
+                if name.startswith("C3"):
+                    # the same data with the tutorial's conditioning (velocity stage on the phase stage's phixy, nu, shape_inv,
+                    # Delta-nu) and the posterior extraction that follows a fit
+                    sec, nbytes = c.posterior_seconds(100, 50)
+                    configs[name]["posterior_100_draws"] = {"seconds": sec, "bytes_to_host": nbytes, "count_bytes_streamed": 0}
+                    configs[name]["conditioned_ms_per_step"] = conditioned_step_ms(a, c, dev)
                 c.close()
             except Exception as exc:  # pragma: no cover
                 configs[name] = {"error": repr(exc)}
@@ -600,6 +677,8 @@ def run_ours(a):
             "api": "the step function of VelocityFitModel.fit (svi.stepper_for -> GraphedSVI.step, one CUDA graph per step"
                    + (", fused step)" if fast else ", traced step)"),
         }
+        if posterior is not None:
+            line["posterior_500_draws_on_device"] = posterior
         if weak is not None:
             line["weak"] = weak
         if parity is not None:

@@ -181,6 +181,41 @@ def test_graphed_svi_matches_eager_svi(kind, use_graph):
         assert float((got[finite] - ref[finite]).abs().max()) <= 5e-3, name
 
 
+@pytest.mark.parametrize("case", ["case_stereo", "case_multi"])
+@pytest.mark.parametrize("kind", ["phase", "phase_nodnu", "velocity", "velocity_lrmn"])
+@pytest.mark.parametrize("conditioned", [False, True])
+def test_batched_posterior_equals_sequential_predictive(case, kind, conditioned):
+    """``sample_posterior`` of the fit drivers (all draws of a bin at once, fastposterior.py) against the sequential
+    ``Predictive`` over the traced guide and model on the same seed: same keys, same shapes, same values (1e-6; the draws
+    themselves are bit-identical).  Also with the tutorial's conditioning."""
+    from velocycle_b200 import phase_inference_model as pm, ppl as pyro, velocity_inference_model as vm
+    from velocycle_b200.likelihood import without_count_sites
+    from velocycle_b200.ppl.infer import Predictive
+
+    z, inp = load(case)
+    mp = _mp(inp, kind)
+    cond = {}
+    if conditioned:
+        draws = section(z, kind, "draw")
+        cond = {k: draws[k].cuda() for k in (("ϕxy", "ν", "shape_inv", "Δν") if kind.startswith("velocity") else ("shape_inv",))
+                if k in draws}
+    Driver = pm.PhaseFitModel if kind.startswith("phase") else vm.VelocityFitModel
+    driver = Driver(mp, condition_on=cond, get_posterior=False)
+    rs = (["ν", "ϕxy", "ϕ", "ζ", "shape_inv"] + (["Δν"] if mp.with_delta_nu else [])) if kind.startswith("phase") \
+        else driver._return_sites()
+    pyro.clear_param_store()
+    pyro.set_rng_seed(9)
+    with without_count_sites():
+        ref = {k: v.cpu() for k, v in Predictive(driver.model, guide=driver.guide, num_samples=3, return_sites=rs)(mp).items()}
+    pyro.set_rng_seed(9)
+    got = driver._batched_posterior(mp, 3, rs)
+    assert got is not None and set(got) == set(ref), (set(got or ()), set(ref))
+    for k in ref:
+        assert tuple(got[k].shape) == tuple(ref[k].shape), (k, tuple(got[k].shape), tuple(ref[k].shape))
+        assert torch.allclose(got[k], ref[k], rtol=1e-6, atol=1e-6), k
+    assert torch.equal(got["ϕxy"], ref["ϕxy"])
+
+
 @pytest.mark.parametrize("kind", ["phase", "velocity_lrmn"])
 def test_posterior_draws_touch_no_counts_and_equal_predictive(kind, monkeypatch):
     """``sample_posterior`` with latent / deterministic ``return_sites`` (what ``fit`` asks for, velocity_inference_model.py:
@@ -205,6 +240,6 @@ def test_posterior_draws_touch_no_counts_and_equal_predictive(kind, monkeypatch)
     assert not calls
     assert set(got) == set(ref)
     for k in ref:
-        assert torch.equal(got[k], ref[k]), k
+        assert torch.allclose(got[k], ref[k], rtol=1e-6, atol=1e-6), k
     driver.sample_posterior(num_samples=1, rs=None)  # the default (every latent site) keeps the full model
     assert calls

@@ -162,6 +162,9 @@ class PhaseFitModel:
     def sample_posterior(self, num_samples=1, rs=None, mp=None):
         _, _, _, infer, _ = backend.get()
         mp = self.metaparams if mp is None else mp
+        fast = self._batched_posterior(mp, num_samples, rs)
+        if fast is not None:
+            return fast
         pred = infer.Predictive(self.model, guide=self.guide, num_samples=num_samples,
                                 return_sites=() if rs is None else rs)
         if rs is not None and "S" not in rs:
@@ -169,6 +172,22 @@ class PhaseFitModel:
                 out = pred(mp)
         else:
             out = pred(mp)
+        return {k: v.cpu() for k, v in out.items()}
+
+    def _batched_posterior(self, mp, num_samples, rs):
+        """The requested sites for all draws at once (``fastposterior.batched_posterior``) when model and guide are the
+        package's own (possibly conditioned) and only latent / deterministic sites are asked for."""
+        from . import ppl as shim
+        from .faststep import model_code
+        from .fastposterior import batched_posterior
+
+        pyro, _, _, _, _ = backend.get()
+        if rs is None or "S" in rs or pyro is not shim or torch.device(mp.device).type != "cuda":
+            return None
+        found = model_code(self.model, self.guide, mp)
+        if found is None:
+            return None
+        out = batched_posterior(mp, found[0], found[1], num_samples, rs)
         return {k: v.cpu() for k, v in out.items()}
 
     def _check_model(self, m, *args):

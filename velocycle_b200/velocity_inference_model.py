@@ -68,7 +68,10 @@ def _velocity_model(mp, lrmn: bool):
     nuw = nu_omega.reshape(mp.Nx, mp.Nhω)
     # per-cell angular speed for the record (tiny); the kernel recomputes it from nu_omega so that its
     # gradient joins the single fused backward
-    cid = counts.cond_id.long() if counts.cond_id is not None else torch.zeros(mp.Nc, dtype=torch.long, device=dev)
+    if counts.cond_id is None:
+        cid = torch.zeros(mp.Nc, dtype=torch.long, device=dev)
+    else:  # ids in the caller's cell order (PackedCounts may hold the rows sorted by batch)
+        cid = (counts.cond_id if counts.perm is None else counts.cond_id[counts.inv_perm]).long()
     pyro.deterministic("ω", (nuw.detach()[cid] * zeta_omega.detach().T).sum(-1).unsqueeze(0))
     if not count_sites_enabled():  # posterior draws of latent / deterministic sites: no pass over the counts
         return
@@ -209,6 +212,9 @@ class VelocityFitModel:
     def sample_posterior(self, num_samples=1, rs=None, mp=None, take_mean=True):
         _, _, _, infer, _ = backend.get()
         mp = self.metaparams if mp is None else mp
+        fast = self._batched_posterior(mp, num_samples, rs)
+        if fast is not None:
+            return fast
         pred = infer.Predictive(self.model, guide=self.guide, num_samples=num_samples,
                                 return_sites=() if rs is None else rs)
         if rs is not None and not ({"S", "U"} & set(rs)):
@@ -216,6 +222,22 @@ class VelocityFitModel:
                 out = pred(mp)
         else:
             out = pred(mp)
+        return {k: v.cpu() for k, v in out.items()}
+
+    def _batched_posterior(self, mp, num_samples, rs):
+        """The requested sites for all draws at once (``fastposterior.batched_posterior``) when model and guide are the
+        package's own (possibly conditioned the tutorial way) and only latent / deterministic sites are asked for."""
+        from . import ppl as shim
+        from .faststep import model_code
+        from .fastposterior import batched_posterior
+
+        pyro, _, _, _, _ = backend.get()
+        if rs is None or ({"S", "U"} & set(rs)) or pyro is not shim or torch.device(mp.device).type != "cuda":
+            return None
+        found = model_code(self.model, self.guide, mp)
+        if found is None:
+            return None
+        out = batched_posterior(mp, found[0], found[1], num_samples, rs, counts=packed_counts_for(mp, need_U=found[0] != 0))
         return {k: v.cpu() for k, v in out.items()}
 
     def _check_model(self, m, *args):
