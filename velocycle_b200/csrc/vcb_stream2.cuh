@@ -18,10 +18,11 @@
 //     one more MMA on a tensor pipe that was 20 % busy;
 //   * per-cell sums (d/dphi, d/dcf, d/domega) are accumulated per cell in scalar registers straight from the
 //     accumulator fragments: no re-pairing moves;
-//   * batch offsets: cells arrive sorted by batch and padded to whole stages (PackedCounts does that once per
-//     dataset), d/dDelta-nu of a (split, batch, gene) is written by the one thread that owns the gene: no atomics,
-//     bit-reproducible.  A stage whose 16 cells disagree (a C-ABI caller with unsorted ids) is processed once per
-//     batch present with the other cells masked out -- slow, correct and still deterministic;
+//   * batch offsets: cells arrive sorted by batch (PackedCounts sorts the rows once per dataset), the offsets are
+//     switched at stage boundaries, d/dDelta-nu of a (split, batch, gene) is written by the one thread that owns the
+//     gene: no atomics, bit-reproducible.  A stage whose 16 cells disagree (the Nb - 1 batch boundaries of sorted data,
+//     or every stage of a C-ABI caller with unsorted ids) is processed once per batch present with the other cells
+//     masked out -- slow, correct and still deterministic;
 //   * no debug branches, no NPAIR / inline-lgamma variants (those calls keep using vcb_stream.cuh).
 #pragma once
 #include "vcb_stream.cuh"
