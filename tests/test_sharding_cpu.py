@@ -69,6 +69,18 @@ def _worker(rank, world, port, tmp):
     gathered = [torch.zeros_like(gene_noise) for _ in range(world)]
     dist.all_gather(gathered, gene_noise)
     assert all(torch.equal(g, gathered[0]) for g in gathered)
+    # the fit drivers' early-exit decision is rank 0's on every rank (a rank leaving the loop alone would hang the others in
+    # the step's all-reduce); PeerComm declines politely where there is no CUDA device / a single rank
+    import collections
+
+    from velocycle_b200.sharding import PeerComm
+    from velocycle_b200.svi import agree_across_ranks
+
+    MP = collections.namedtuple("MP", "shard device")
+    assert agree_across_ranks(rank == 0, MP(shard, "cpu")) is True
+    assert agree_across_ranks(rank != 0, MP(shard, "cpu")) is False
+    assert agree_across_ranks(True, MP(None, "cpu")) is True
+    assert PeerComm.create(ShardInfo(0, 1, 0, Nc), 128, "cpu") is None
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
