@@ -802,12 +802,7 @@ static Plan2 make_plan2(const vcb_problem_t* p, bool velo) {
   pl.tabg = table_group_floats(p->H, velo);
   pl.rows = gene_rows(p->H);
   pl.NQ = velo ? 3 : 2;
-  pl.n_ring = 2;
-  for (int r = s2::kMaxNS; r >= 2; --r)
-    if (s2::smem_layout(p->H, velo, s2::kThreads / 32, r).total <= kSmemBudget - 1024) {
-      pl.n_ring = r;
-      break;
-    }
+  pl.n_ring = s2::ring_depth(p->H, velo);  // the kernel computes the same depth from its template arguments
   pl.smem = s2::smem_layout(p->H, velo, s2::kThreads / 32, pl.n_ring).total;
   size_t off = 0;
   pl.off_tab = off;

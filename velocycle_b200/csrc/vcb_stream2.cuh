@@ -62,8 +62,8 @@ struct Smem {
   int part_off, gene_off, aop_off, tab_off, cnt_off, total;
 };
 
-__host__ __device__ inline Smem smem_layout(int H, bool velo, int nwarps, int n_ring) {
-  Smem L;
+__host__ __device__ constexpr Smem smem_layout(int H, bool velo, int nwarps, int n_ring) {
+  Smem L{};
   int off = kHeader;
   L.part_off = off;  // cell partials: [park slot][group][warp][quantity][cell], park ring = table ring + 2 stages
   off += (n_ring + kSvcDist) * kGPS * nwarps * (velo ? 3 : 2) * 8 * 4;
@@ -78,6 +78,15 @@ __host__ __device__ inline Smem smem_layout(int H, bool velo, int nwarps, int n_
   off += kD * (velo ? 2 : 1) * 2 * (32 * nwarps) * 16;
   L.total = off;
   return L;
+}
+
+// Depth of the table ring: as many stages as the shared memory of one CTA per SM allows -- a function of the template
+// arguments only, so the ring arithmetic of the kernel is compile-time.
+constexpr int kSmemBudget = 226 * 1024;  // of the 227 KB opt-in dynamic shared memory per CTA on sm_100
+__host__ __device__ constexpr int ring_depth(int H, bool velo) {
+  for (int r = kMaxNS; r > 2; --r)
+    if (smem_layout(H, velo, kThreads / 32, r).total <= kSmemBudget) return r;
+  return 2;
 }
 
 template <int H, bool VELO, bool GRAD>
@@ -102,13 +111,13 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   constexpr uint32_t kSlotBytes = (uint32_t)nthr * 16u;  // distance between two of a thread's count slots
   const int warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 2, q = lane & 3;
-  const int NS = P.n_ring;
+  constexpr int NS = ring_depth(H, VELO);
   const int tile = blockIdx.x, split = blockIdx.y;
   constexpr int tile_genes = 32 * nwarps;
   const long long g_base = (long long)tile * tile_genes;
   const long long rem = P.ld - g_base;
   const int W = (int)(rem < (long long)tile_genes ? rem : (long long)tile_genes);
-  const Smem L = smem_layout(H, VELO, nwarps, NS);
+  constexpr Smem L = smem_layout(H, VELO, nwarps, NS);
   const uint32_t full0 = smem_u32(smem_raw);
   const uint32_t done0 = full0 + 8 * kMaxNS;
   float* const s_part = reinterpret_cast<float*>(smem_raw + L.part_off);
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   // the wait returns at once and nobody spins), re-issues the table copy of that slot for stage x + NS, adds the 16 warps'
   // parked terms in a fixed order (deterministic) and stores them.  A warp can be at most NS - 1 stages ahead of the slowest
   // one and the servicing warp two stages behind the stage it serves: the park ring has NS + 2 slots.
-  const int NP = NS + kSvcDist;
+  constexpr int NP = NS + kSvcDist;
   auto service = [&](int x) {
     const int xs = x % NS;
     mbar_wait(done0 + 8 * xs, (uint32_t)((x / NS) & 1));
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
           g = mul2(fma2(nr_mt, u, kS), rcp_2(s));
         }
         if (GRAD) {
-          pcf2[cc] = add2(pcf2[cc], g);
+          pcf2[cc] = mt == 0 ? g : add2(pcf2[cc], g);
           pphi[cc] = fmaf(g.x, Cd[cc], pphi[cc]);
           pphi[cc] = fmaf(g.y, Cd[2 + cc], pphi[cc]);
         }
@@ -457,14 +466,28 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
           if (VELO) mma_tf32(acw, wh, __float_as_uint(bw.z), __float_as_uint(bw.w));
           mma_tf32(acc, gh, __float_as_uint(bz.x), __float_as_uint(bz.y));
           if (VELO) mma_tf32(acw, wh, __float_as_uint(bw.x), __float_as_uint(bw.y));
+#ifdef VCB_EXP_NU2
+#pragma unroll
+          for (int i = 0; i < 4; i += 2) {
+            float2 t = f2(acc[i], acc[i + 1]);
+            if (VELO) t = add2(t, f2(acw[i], acw[i + 1]));
+            const float2 r2 = add2(f2(accNu[mt][nt][i], accNu[mt][nt][i + 1]), t);
+            accNu[mt][nt][i] = r2.x;
+            accNu[mt][nt][i + 1] = r2.y;
+          }
+#else
 #pragma unroll
           for (int i = 0; i < 4; ++i) accNu[mt][nt][i] += VELO ? acc[i] + acw[i] : acc[i];
+#endif
         }
       }
     }
     if (GRAD) {
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) pcf[cc] += pcf2[cc].x + pcf2[cc].y;
+      for (int cc = 0; cc < 2; ++cc) {  // a masked group makes one pass per batch present: those accumulate
+        const float t = pcf2[cc].x + pcf2[cc].y;
+        pcf[cc] = MASKED ? pcf[cc] + t : t;
+      }
     }
   };
 
@@ -474,12 +497,15 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   // one 8-cell group of the current stage: consume, reduce the per-cell sums over the warp's genes, park them, refill the
   // count slot
   int c_ring = 0;  // count-ring slot of the next group to consume (and, once consumed, to refill)
-  auto do_group = [&](auto masked_tag, const int h, const float* tb_stage, float* part_stage) {
+  auto do_group = [&](auto masked_tag, auto staged_tag, const int h, const float* tb_stage, float* part_stage) {
     constexpr bool MASKED = decltype(masked_tag)::value;
-    cp_async_wait<D - 1>();
-    __syncwarp();
+    constexpr bool STAGED = decltype(staged_tag)::value;  // the caller waits for / refills both groups of the stage at once
+    if (!STAGED) {
+      cp_async_wait<D - 1>();
+      __syncwarp();
+    }
     const float* tb = tb_stage + h * TABG;
-    const float4* cnt = s_cnt + (size_t)c_ring * NLD * nthr;
+    const float4* cnt = s_cnt + (size_t)(STAGED ? c_ring + h : c_ring) * NLD * nthr;
     float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
     if (MASKED) {
       // mixed stage: one masked pass per batch present among the 16 cells (warp-uniform decisions)
@@ -515,9 +541,11 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
         if (VELO) part_stage[32 + h] = v2;
       }
     }
-    __syncwarp();  // every lane has read its counts: the slot may be refilled
-    load_counts(c_ring);
-    c_ring = c_ring + 1 == D ? 0 : c_ring + 1;
+    if (!STAGED) {
+      __syncwarp();  // every lane has read its counts: the slot may be refilled
+      load_counts(c_ring);
+      c_ring = c_ring + 1 == D ? 0 : c_ring + 1;
+    }
   };
   // Leave stage st: the tables of the slot and this warp's parked partials are final (the __syncwarp in do_group orders the
   // other lanes' accesses before lane 0's arrival); then the rotating service duty for the stage that starts next.
@@ -543,10 +571,23 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       set_batch(cur_b);
     }
     if (stage_b >= 0) {
+#ifdef VCB_EXP_STG
+      // one wait and one refill per stage: the two groups' loads, MMAs and element math are free to overlap
+      static_assert(D % kGPS == 0, "the count ring holds whole stages");
+      cp_async_wait<D - kGPS>();
+      __syncwarp();
 #pragma unroll
-      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, h, tb_stage, part_stage);
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, BoolTag<true>{}, h, tb_stage, part_stage);
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < kGPS; ++h) load_counts(c_ring + h);
+      c_ring = c_ring + kGPS == D ? 0 : c_ring + kGPS;
+#else
+#pragma unroll
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, BoolTag<false>{}, h, tb_stage, part_stage);
+#endif
     } else {
-      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, h, tb_stage, part_stage);
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, BoolTag<false>{}, h, tb_stage, part_stage);
     }
     leave_stage(st);
   }
