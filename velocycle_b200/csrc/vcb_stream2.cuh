@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
           if (VELO) mma_tf32(acw, wh, __float_as_uint(bw.z), __float_as_uint(bw.w));
           mma_tf32(acc, gh, __float_as_uint(bz.x), __float_as_uint(bz.y));
           if (VELO) mma_tf32(acw, wh, __float_as_uint(bw.x), __float_as_uint(bw.y));
-#ifdef VCB_EXP_NU2
+          // packed adds on the accumulator pairs (c0,c1), (c2,c3): with scalar adds the register allocator scattered accNu over
+          // odd registers and re-paired every FFMA2 operand around them with MOVs (97 -> 22 MOVs per stage, -6 % time)
 #pragma unroll
           for (int i = 0; i < 4; i += 2) {
             float2 t = f2(acc[i], acc[i + 1]);
@@ -475,10 +476,6 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
             accNu[mt][nt][i] = r2.x;
             accNu[mt][nt][i + 1] = r2.y;
           }
-#else
-#pragma unroll
-          for (int i = 0; i < 4; ++i) accNu[mt][nt][i] += VELO ? acc[i] + acw[i] : acc[i];
-#endif
         }
       }
     }
@@ -497,15 +494,12 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
   // one 8-cell group of the current stage: consume, reduce the per-cell sums over the warp's genes, park them, refill the
   // count slot
   int c_ring = 0;  // count-ring slot of the next group to consume (and, once consumed, to refill)
-  auto do_group = [&](auto masked_tag, auto staged_tag, const int h, const float* tb_stage, float* part_stage) {
+  auto do_group = [&](auto masked_tag, const int h, const float* tb_stage, float* part_stage) {
     constexpr bool MASKED = decltype(masked_tag)::value;
-    constexpr bool STAGED = decltype(staged_tag)::value;  // the caller waits for / refills both groups of the stage at once
-    if (!STAGED) {
-      cp_async_wait<D - 1>();
-      __syncwarp();
-    }
+    cp_async_wait<D - 1>();
+    __syncwarp();
     const float* tb = tb_stage + h * TABG;
-    const float4* cnt = s_cnt + (size_t)(STAGED ? c_ring + h : c_ring) * NLD * nthr;
+    const float4* cnt = s_cnt + (size_t)c_ring * NLD * nthr;
     float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
     if (MASKED) {
       // mixed stage: one masked pass per batch present among the 16 cells (warp-uniform decisions)
@@ -541,11 +535,9 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
         if (VELO) part_stage[32 + h] = v2;
       }
     }
-    if (!STAGED) {
-      __syncwarp();  // every lane has read its counts: the slot may be refilled
-      load_counts(c_ring);
-      c_ring = c_ring + 1 == D ? 0 : c_ring + 1;
-    }
+    __syncwarp();  // every lane has read its counts: the slot may be refilled
+    load_counts(c_ring);
+    c_ring = c_ring + 1 == D ? 0 : c_ring + 1;
   };
   // Leave stage st: the tables of the slot and this warp's parked partials are final (the __syncwarp in do_group orders the
   // other lanes' accesses before lane 0's arrival); then the rotating service duty for the stage that starts next.
@@ -571,23 +563,10 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       set_batch(cur_b);
     }
     if (stage_b >= 0) {
-#ifdef VCB_EXP_STG
-      // one wait and one refill per stage: the two groups' loads, MMAs and element math are free to overlap
-      static_assert(D % kGPS == 0, "the count ring holds whole stages");
-      cp_async_wait<D - kGPS>();
-      __syncwarp();
 #pragma unroll
-      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, BoolTag<true>{}, h, tb_stage, part_stage);
-      __syncwarp();
-#pragma unroll
-      for (int h = 0; h < kGPS; ++h) load_counts(c_ring + h);
-      c_ring = c_ring + kGPS == D ? 0 : c_ring + kGPS;
-#else
-#pragma unroll
-      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, BoolTag<false>{}, h, tb_stage, part_stage);
-#endif
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, h, tb_stage, part_stage);
     } else {
-      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, BoolTag<false>{}, h, tb_stage, part_stage);
+      for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, h, tb_stage, part_stage);
     }
     leave_stage(st);
   }
