@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
     for (int i = 1; i < kGroupCells; ++i)
       if (__float_as_int(s_tail[warp][8 + i]) != b) b = -1;
     if (P.v2 && P.batch_id != nullptr) {  // the whole 16-cell stage must agree (padding cells copy the last cell)
-      const long long c0 = (group & ~1ll) * kGroupCells;
+      const long long c0 = (group / s2::kGPS) * s2::kStageCells;
       for (int i = 0; i < s2::kStageCells; ++i) {
         const long long c = c0 + i < P.Nc ? c0 + i : P.Nc - 1;
         if (P.batch_id[c] != b) b = -1;

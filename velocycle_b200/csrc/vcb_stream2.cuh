@@ -4,7 +4,7 @@
 // by the TMA engine -- rebuilt around the round-1 profile (profiles/r01_stream_kernel_ncu_summary.txt): that kernel
 // was issue bound, 475 warp instructions per warp and 8-cell group of which ~190 were bookkeeping.  What changed:
 //
-//   * a ring stage is TWO 8-cell groups (16 cells): one table copy, one full[] wait, one done[] arrival, one batch
+//   * a ring stage is kGPS = 2 8-cell groups (16 cells): one table copy, one full[] wait, one done[] arrival, one batch
 //     test and one issue test per 16 cells;
 //   * stage service by rotation: warp (x + 2) % 16 services stage x when it enters stage x + 2 -- it waits on the done[]
 //     mbarrier of x (all 16 warps have arrived; normally long ago), re-issues the slot's table copy for stage x + NS and
@@ -30,13 +30,20 @@
 namespace vcb {
 namespace s2 {
 
-constexpr int kGPS = 2;                          // 8-cell groups per ring stage
+#ifdef VCB_EXP_GPS
+constexpr int kGPS = VCB_EXP_GPS;
+#else
+// 8-cell groups per ring stage.  4 (with the ring depth halved: same shared memory, half the per-stage bookkeeping) loses 4 %:
+// the servicing warp then waits for the slowest warp every stage and the warps run in lockstep through the same phases.
+constexpr int kGPS = 2;
+#endif
 constexpr int kStageCells = kGPS * kGroupCells;  // 16
 constexpr int kD = 4;                            // count groups in flight per warp
 constexpr int kMaxNS = 8;                        // table-ring depth limit (mbarrier slots)
 constexpr int kThreads = 512;  // 16 warps x 128 registers: 20-24 warps at 80-96 registers spill and lose 30 % (tried)
 constexpr int kHeader = 256;
-constexpr int kSvcDist = 2;  // a stage is serviced (table slot refilled, parked cell partials drained) this many stages later
+// a stage is serviced (table slot refilled, parked cell partials drained) this many stages later
+constexpr int kSvcDist = kGPS >= 4 ? 1 : 2;
 constexpr float kRelEps = 1e-5f;
 
 struct Params {
@@ -57,6 +64,10 @@ struct Params {
   int Nb;
   int n_ring;
 };
+
+template <int N> struct GroupVec;
+template <> struct GroupVec<2> { using type = float2; };
+template <> struct GroupVec<4> { using type = float4; };
 
 struct Smem {
   int part_off, gene_off, aop_off, tab_off, cnt_off, total;
@@ -296,17 +307,21 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     if (lane == 0 && x + NS < n_stages) issue_stage(x + NS, xs);
     if (GRAD && lane < R * NQ) {
       const int i = lane >> 3, cell = lane & 7;
-      const float2* src = reinterpret_cast<const float2*>(s_part) + (size_t)(x % NP) * nwarps * (NQ * 8) + lane;
-      float2 s = make_float2(0.f, 0.f);
+      using VecG = typename GroupVec<kGPS>::type;  // one (quantity, cell) of every group of the stage
+      const VecG* src = reinterpret_cast<const VecG*>(s_part) + (size_t)(x % NP) * nwarps * (NQ * 8) + lane;
+      float s[kGPS];
+#pragma unroll
+      for (int g = 0; g < kGPS; ++g) s[g] = 0.f;
 #pragma unroll
       for (int w = 0; w < nwarps; ++w) {
-        const float2 v = src[w * (NQ * 8)];
-        s.x += v.x;
-        s.y += v.y;
+        const VecG v = src[w * (NQ * 8)];
+        const float* vf = reinterpret_cast<const float*>(&v);
+#pragma unroll
+        for (int g = 0; g < kGPS; ++g) s[g] += vf[g];
       }
       float* dst = cellpart_t + (T0 + x) * (long long)(kGPS * R * NQ) + cell * NQ + i;
-      dst[0] = s.x;
-      dst[R * NQ] = s.y;
+#pragma unroll
+      for (int g = 0; g < kGPS; ++g) dst[g * R * NQ] = s[g];
     }
   };
 #pragma unroll
@@ -503,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     float pcf[2] = {0.f, 0.f}, pphi[2] = {0.f, 0.f}, pom[2] = {0.f, 0.f};
     if (MASKED) {
       // mixed stage: one masked pass per batch present among the 16 cells (warp-uniform decisions)
-      const int my_id = __float_as_int(tb_stage[(lane >> 3 & 1) * TABG + TAIL + 8 + (lane & 7)]);
+      const int my_id = __float_as_int(tb_stage[((lane >> 3) & (kGPS - 1)) * TABG + TAIL + 8 + (lane & 7)]);
       for (int b = 0; b < P.Nb; ++b) {
         if (!__any_sync(0xffffffffu, my_id == b)) continue;
         if (b != cur_b) {
@@ -531,8 +546,8 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       if (VELO) v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
       if ((lane & 12) == 0) {
         part_stage[h] = v0;
-        part_stage[16 + h] = v1;
-        if (VELO) part_stage[32 + h] = v2;
+        part_stage[8 * kGPS + h] = v1;
+        if (VELO) part_stage[16 * kGPS + h] = v2;
       }
     }
     __syncwarp();  // every lane has read its counts: the slot may be refilled
@@ -555,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     mbar_wait(full0 + 8 * c_slot, (uint32_t)c_phase);
     const float* tb_stage = s_tab + (size_t)c_slot * (kGPS * TABG);
     // park address of this lane's cell: [p_slot][warp][quantity][cell][group]
-    float* part_stage = s_part + (((size_t)p_slot * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4))) * 2;
+    float* part_stage = s_part + (((size_t)p_slot * nwarps + warp) * (NQ * 8) + (q + 4 * (lane >> 4))) * kGPS;
     const int stage_b = __float_as_int(tb_stage[TAIL + 16]);  // the stage's batch (0 without batches), -1 if its cells disagree
     if (stage_b != cur_b && stage_b >= 0) {
       if (GRAD) flush_batch();
