@@ -64,33 +64,47 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
   const long long group = (long long)(blockIdx.x - P.n_spec_blocks) * kTabWarps + warp;
   if (group >= P.n_groups) return;
   const int H = P.H, K = 2 * H + 1, KS = ksteps(H);
+  {  // clear the warp's staging block with all 32 lanes (160 float4)
+    float4* z = reinterpret_cast<float4*>(&sv[warp][0][0][0]);
+#pragma unroll
+    for (int i = 0; i < 5 * kGroupCells * kTabSlots / 4 / 32; ++i) z[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
   if (lane < kGroupCells) {
     const long long c = group * kGroupCells + lane;
     const bool valid = c < P.Nc;
     const long long cl = valid ? c : P.Nc - 1;  // padding cells copy the batch of the last cell
     const float phi = valid ? P.phi[c] : 0.f;
+    // sin / cos of the harmonics: one accurate sincosf, the multiples by the angle-addition recurrence (a few ulp at n = 5)
+    float sn[VCB_MAX_HARMONICS + 1], cn[VCB_MAX_HARMONICS + 1];
+    sn[0] = 0.f;
+    cn[0] = 1.f;
+    sincosf(phi, &sn[1], &cn[1]);
+#pragma unroll
+    for (int n = 2; n <= VCB_MAX_HARMONICS; ++n) {
+      sn[n] = fmaf(sn[n - 1], cn[1], cn[n - 1] * sn[1]);
+      cn[n] = fmaf(cn[n - 1], cn[1], -sn[n - 1] * sn[1]);
+    }
     float omega = 0.f;
     if (P.velo && P.nu_omega != nullptr) {
       const int x = P.cond_id ? P.cond_id[cl] : 0;
       const int Kw = 2 * P.Hw + 1;
       const float* nw = P.nu_omega + (long long)x * Kw;
       omega = nw[0];
-      for (int n = 1; n <= P.Hw; ++n) {
-        float s, co;
-        sincosf((float)n * phi, &s, &co);
-        omega = fmaf(nw[2 * n - 1], s, omega);
-        omega = fmaf(nw[2 * n], co, omega);
-      }
+#pragma unroll
+      for (int n = 1; n <= VCB_MAX_HARMONICS; ++n)
+        if (n <= P.Hw) {
+          omega = fmaf(nw[2 * n - 1], sn[n], omega);
+          omega = fmaf(nw[2 * n], cn[n], omega);
+        }
     }
     float(*v)[kGroupCells][kTabSlots] = sv[warp];
-    for (int sec = 0; sec < 5; ++sec)
-      for (int k = 0; k < kTabSlots; ++k) v[sec][lane][k] = 0.f;
     v[0][lane][0] = 1.f;
     v[3][lane][0] = 1.f;
-    for (int n = 1; n <= H; ++n) {
-      float s, co;
-      const float fn = (float)n;
-      sincosf(fn * phi, &s, &co);
+#pragma unroll
+    for (int n = 1; n <= VCB_MAX_HARMONICS; ++n) {
+      if (n > H) break;
+      const float fn = (float)n, s = sn[n], co = cn[n];
       const int ks = 2 * n - 1, kc = 2 * n;
       v[0][lane][ks] = s;
       v[0][lane][kc] = co;
