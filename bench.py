@@ -582,7 +582,7 @@ def run_ours(a):
     clocks = stop_clock_sampler(sampler, path) if rank == 0 else None
     value = Nc * world * Ng / (ms_per_step * 1e-3)
     roofline = w.roofline(kern)
-    roofline["note"] = ("issue-slot / latency bound at 16 warps per SM, not HBM bound: no pipe above 46 % busy (DESIGN.md "
+    roofline["note"] = ("latency / pipe-contention bound at 16 warps per SM, not HBM bound: no pipe above 50 % busy (DESIGN.md "
                         "section 4, profiles/r02_stream_kernel_ncu_summary.txt)")
     breakdown = w.breakdown()
     zero_S, zero_U = w.zero_S, w.zero_U

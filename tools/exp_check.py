@@ -33,5 +33,5 @@ for tag, Nc, Ng, Nb, velo in (("v", 30001, 2000, 1, True), ("vb", 20011, 1000, 5
     out = fused_elbo_grad(*args, grad=True)
     torch.cuda.synchronize()
     for k, v in out.items():
-        if torch.is_tensor(v): res[f"{tag}.{k}"] = v.detach().cpu()
+        if torch.is_tensor(v) and not k.startswith("_"): res[f"{tag}.{k}"] = v.detach().cpu()  # ("_workspace" is scratch)
 torch.save(res, sys.argv[3])
