@@ -214,6 +214,20 @@ def test_batched_posterior_equals_sequential_predictive(case, kind, conditioned)
         assert tuple(got[k].shape) == tuple(ref[k].shape), (k, tuple(got[k].shape), tuple(ref[k].shape))
         assert torch.allclose(got[k], ref[k], rtol=1e-6, atol=1e-6), k
     assert torch.equal(got["ϕxy"], ref["ϕxy"])
+    # the layout Pyro's Predictive produces (tests/test_predictive_shapes_cpu.py): singleton dims up to the model's plate
+    # nesting minus the site's own batch dims.  Nesting: cells -1, genes -2, [harmonics -3, conditions -4 in the velocity
+    # model,] batches -3 / -5 -- entered only with Δν
+    Ng, Nc, K = int(mp.Ng), int(mp.Nc), int(mp.μνg.shape[-1])
+    if kind.startswith("phase"):
+        mpn = 3 if mp.with_delta_nu else 2
+        sites = {"ν": (2, (Ng, 1, K)), "ϕ": (0, (Nc,)), "ϕxy": (1, (Nc, 2))}
+    else:
+        mpn = 5 if mp.with_delta_nu else 4
+        sites = {"ν": (2, (Ng, 1, K)), "ϕ": (0, (Nc,)), "γg": (2, (Ng, 1)), "νω": (4, (int(mp.Nx), int(mp.Nhω), 1, 1)),
+                 "ϕxy": (1, (Nc, 2))}
+    for k, (bdim, vshape) in sites.items():
+        want = (3,) + (1,) * (mpn - bdim) + vshape
+        assert tuple(got[k].shape) == want, (k, tuple(got[k].shape), want)
 
 
 @pytest.mark.parametrize("kind", ["phase", "velocity_lrmn"])

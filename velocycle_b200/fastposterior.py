@@ -31,9 +31,10 @@ def _cond_ids(counts, Nc: int, dev) -> torch.Tensor:
 
 @torch.no_grad()
 def batched_posterior(mp, code: int, conditioned: Optional[dict], num_samples: int, return_sites: Iterable[str],
-                      counts=None) -> Dict[str, torch.Tensor]:
-    """``{site: (num_samples, *site_shape)}`` on ``mp.device`` for the sites of ``return_sites`` that the model defines;
-    ``code`` / ``conditioned`` as returned by ``faststep.model_code``."""
+                      counts=None, pad: Optional[Dict[str, int]] = None) -> Dict[str, torch.Tensor]:
+    """``{site: (num_samples, 1, ..., 1, *site_shape)}`` on ``mp.device`` for the sites of ``return_sites`` that the model
+    defines; ``code`` / ``conditioned`` as returned by ``faststep.model_code``; ``pad[site]`` = the number of singleton dims
+    ``Predictive`` puts behind the sample dim (``ppl.infer.predictive_padding``; none when ``pad`` is None)."""
     pyro, _, _, _, _ = backend.get()
     dev = torch.device(mp.device)
     n, rs, cond = int(num_samples), set(return_sites), dict(conditioned or {})
@@ -121,4 +122,5 @@ def batched_posterior(mp, code: int, conditioned: Optional[dict], num_samples: i
                     cid = _cond_ids(counts, Nc, dev)
                     nw = nuw.reshape(n, int(mp.Nx), int(mp.Nhω))
                     out["ω"] = (nw[:, cid, :] * zw).sum(-1).unsqueeze(1)
-    return {k: v for k, v in out.items() if k in rs}
+    pad = pad or {}
+    return {k: v.reshape((n,) + (1,) * int(pad.get(k, 0)) + tuple(v.shape[1:])) for k, v in out.items() if k in rs}

@@ -147,9 +147,52 @@ class SVI:
         return torch_item(loss)
 
 
+def _batch_ndim(site: dict) -> int:
+    """Length of the site distribution's batch shape as Pyro's BroadcastMessenger leaves it: plates expand every sample
+    site -- ``pyro.deterministic`` sites included, whose Delta starts with an empty batch shape -- up to their dim."""
+    n = len(getattr(site["fn"], "batch_shape", ()))
+    for frame in site["cond_indep_stack"]:
+        n = max(n, -frame.dim)
+    return n
+
+
+def predictive_site_shapes(model_trace, num_samples: int, return_sites, posterior_names=()) -> Dict[str, tuple]:
+    """Which sites ``Predictive`` returns and the shape of each: Pyro 1.8.6 ``pyro/infer/predictive.py`` (``_predictive``):
+    ``(num_samples,) + (1,) * (max_plate_nesting - len(fn.batch_shape)) + value.shape`` for the sites in ``return_sites``;
+    every sample site (latent, observed, deterministic) when ``return_sites`` is None; the sites that are not among the
+    posterior samples when it is empty."""
+    sites = [(k, v) for k, v in model_trace.nodes.items() if v["type"] == "sample"]
+    dims = [frame.dim for _, v in sites for frame in v["cond_indep_stack"]]
+    mpn = -min(dims) if dims else 0
+    shapes: Dict[str, tuple] = {}
+    for name, site in sites:
+        shape = (int(num_samples),) + (1,) * (mpn - _batch_ndim(site)) + tuple(site["value"].shape)
+        if return_sites:
+            if name in return_sites:
+                shapes[name] = shape
+        elif return_sites is None or name not in posterior_names:
+            shapes[name] = shape
+    return shapes
+
+
+def predictive_padding(model, guide, *args, device=None, **kwargs) -> Dict[str, int]:
+    """site -> number of singleton dims ``Predictive`` inserts behind the sample dim (``predictive_site_shapes``), from
+    one guide trace and model replay that leave the RNG state untouched."""
+    dev = None if device is None else torch.device(device)
+    devices = [dev.index if dev.index is not None else torch.cuda.current_device()] if dev is not None and dev.type == "cuda" else []
+    with torch.random.fork_rng(devices=devices), torch.no_grad():
+        guide_trace = poutine.trace(guide).get_trace(*args, **kwargs)
+        model_trace = poutine.trace(poutine.replay(model, trace=guide_trace)).get_trace(*args, **kwargs)
+    shapes = predictive_site_shapes(model_trace, 1, None)
+    return {k: len(shape) - 1 - model_trace.nodes[k]["value"].dim() for k, shape in shapes.items()}
+
+
 class Predictive:
     """Sequential ``Predictive(model, guide=guide, num_samples=N, return_sites=...)`` as used by the fit drivers
-    (``velocity_inference_model.py:279-291``): draw the guide, replay the model, collect the requested sites."""
+    (``velocity_inference_model.py:279-291``): draw the guide, replay the model, collect the requested sites.  Site selection
+    and output shapes follow Pyro 1.8.6 (``predictive_site_shapes``): with a guide and no ``return_sites`` every model site
+    comes back, and every value is left-padded with singleton dims up to the model's plate nesting.  (Pyro spends two guide
+    and two model executions on shape discovery before the draws; that RNG consumption is not reproduced.)"""
 
     def __init__(self, model, posterior_samples=None, guide=None, num_samples=None, return_sites=(), parallel=False):
         if parallel:
@@ -166,24 +209,25 @@ class Predictive:
         n = self.num_samples
         if n is None:
             n = next(iter(self.posterior_samples.values())).shape[0]
+        return_sites = self.return_sites
+        if self.guide is not None and not return_sites:
+            return_sites = None  # "return all sites by default if a guide is provided"
+        shapes = None
         collected: Dict[str, list] = {}
         for i in range(n):
             if self.guide is not None:
                 guide_trace = poutine.trace(self.guide).get_trace(*args, **kwargs)
                 model_trace = poutine.trace(poutine.replay(self.model, trace=guide_trace)).get_trace(*args, **kwargs)
+                names = [k for k, v in guide_trace.nodes.items() if v["type"] == "sample"]
             else:
                 data = {k: v[i] for k, v in (self.posterior_samples or {}).items()}
                 model_trace = poutine.trace(poutine.condition(self.model, data=data)).get_trace(*args, **kwargs)
-            for name, site in model_trace.nodes.items():
-                if site["type"] != "sample":
-                    continue
-                if self.return_sites:
-                    keep = name in self.return_sites
-                else:  # default: latent sample sites only
-                    keep = not site["is_observed"]
-                if keep:
-                    collected.setdefault(name, []).append(site["value"].detach())
-        return {k: torch.stack(v) for k, v in collected.items()}
+                names = list(data)
+            if shapes is None:
+                shapes = predictive_site_shapes(model_trace, n, return_sites, names)
+            for name in shapes:
+                collected.setdefault(name, []).append(model_trace.nodes[name]["value"].detach())
+        return {k: torch.stack(v).reshape(shapes[k]) for k, v in collected.items()}
 
     forward = __call__
 

@@ -237,7 +237,10 @@ class VelocityFitModel:
         found = model_code(self.model, self.guide, mp)
         if found is None:
             return None
-        out = batched_posterior(mp, found[0], found[1], num_samples, rs, counts=packed_counts_for(mp, need_U=found[0] != 0))
+        with without_count_sites():  # output shapes as Predictive pads them (one count-free trace, RNG state untouched)
+            pad = shim.infer.predictive_padding(self.model, self.guide, mp, device=mp.device)
+        out = batched_posterior(mp, found[0], found[1], num_samples, rs, counts=packed_counts_for(mp, need_U=found[0] != 0),
+                                pad=pad)
         return {k: v.cpu() for k, v in out.items()}
 
     def _check_model(self, m, *args):
