@@ -179,6 +179,141 @@ __global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables_kernel(const C
   if (lane < 20) P.tab[group * P.tabg + table_tail(H, P.velo != 0) + lane] = s_tail[warp][lane];
 }
 
+// ------------------------------------------------------------------------------------------------------
+// The same tables for vcb_stream2.cuh (one k-step, H <= 3), four groups per warp: every lane owns one of the warp's 32 cells
+// for the per-cell part (one sincosf, the higher harmonics by recurrence, omega), then the warp emits the four groups'
+// fragments.  The one-group kernel above ran its per-cell part on 8 of 32 lanes; this one needs less than half the
+// instructions per group.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kTab4Groups = 4;
+constexpr int kTab4Pitch = 9;  // 8 slots + 1: the per-cell writes of a warp (stride = one cell) hit 32 different banks
+
+__global__ void __launch_bounds__(kTabWarps * 32) vcb_cell_tables4_kernel(const CellParams P) {
+  // sections [0] zeta (forward eta operand; the backward zeta is the same with the spare slot cleared), [1] zeta',
+  // [2] omega*zeta'', [3] omega*zeta'
+  __shared__ float sv[kTabWarps][kTab4Groups][4][kGroupCells][kTab4Pitch];
+  __shared__ float s_tail[kTabWarps][kTab4Groups][20];
+  if (blockIdx.x < P.n_spec_blocks) {
+    spectrum_block(P, blockIdx.x);
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long group0 = ((long long)(blockIdx.x - P.n_spec_blocks) * kTabWarps + warp) * kTab4Groups;
+  if (group0 >= P.n_groups) return;
+  const int H = P.H, K = 2 * H + 1;
+  {  // ---- per cell: lane = (group gi, cell ci) -------------------------------------------------------------------------
+    const int gi = lane >> 3, ci = lane & 7;
+    const long long c = group0 * kGroupCells + lane;
+    const bool valid = c < P.Nc;
+    const long long cl = valid ? c : P.Nc - 1;  // padding cells copy the batch of the last cell
+    const float phi = valid ? P.phi[c] : 0.f;
+    float sn[4], cn[4];  // harmonics 1..3 (slot 0 unused)
+    sincosf(phi, &sn[1], &cn[1]);
+#pragma unroll
+    for (int n = 2; n <= 3; ++n) {
+      sn[n] = fmaf(sn[n - 1], cn[1], cn[n - 1] * sn[1]);
+      cn[n] = fmaf(cn[n - 1], cn[1], -sn[n - 1] * sn[1]);
+    }
+    float omega = 0.f;
+    if (P.velo && P.nu_omega != nullptr) {
+      const int x = P.cond_id ? P.cond_id[cl] : 0;
+      const float* nw = P.nu_omega + (long long)x * (2 * P.Hw + 1);
+      omega = nw[0];
+#pragma unroll
+      for (int n = 1; n <= 3; ++n)
+        if (n <= P.Hw) {
+          omega = fmaf(nw[2 * n - 1], sn[n], omega);
+          omega = fmaf(nw[2 * n], cn[n], omega);
+        }
+      for (int n = 4; n <= P.Hw; ++n) {
+        float s, co;
+        sincosf((float)n * phi, &s, &co);
+        omega = fmaf(nw[2 * n - 1], s, omega);
+        omega = fmaf(nw[2 * n], co, omega);
+      }
+    }
+    float v[4][8];  // all 8 slots of every section are written
+#pragma unroll
+    for (int sec = 0; sec < 4; ++sec)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[sec][k] = 0.f;
+    v[0][0] = 1.f;
+#pragma unroll
+    for (int n = 1; n <= 3; ++n)
+      if (n <= H) {
+        const float fn = (float)n, s = sn[n], co = cn[n];
+        const int ks = 2 * n - 1, kc = 2 * n;
+        v[0][ks] = s;
+        v[0][kc] = co;
+        v[1][ks] = fn * co;
+        v[1][kc] = -fn * s;
+        v[3][ks] = omega * (fn * co);
+        v[3][kc] = omega * (-fn * s);
+        v[2][ks] = omega * (-fn * fn * s);
+        v[2][kc] = omega * (-fn * fn * co);
+      }
+    // spare slot K: the size factor rides the forward contraction; a padding cell gets eta = -3e4; backward: sum_c w = d/dgamma
+    const float spare0 = valid ? (P.cf ? P.cf[c] : 0.f) : -30000.f;
+#pragma unroll
+    for (int k = 1; k < 8; k += 2)  // K is odd
+      if (k == K) {
+        v[0][k] = spare0;
+        v[3][k] = 1.f;
+      }
+#pragma unroll
+    for (int sec = 0; sec < 4; ++sec)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sv[warp][gi][sec][ci][k] = v[sec][k];
+    const int bid = P.batch_id ? P.batch_id[cl] : 0;
+    s_tail[warp][gi][ci] = omega * kLn2;
+    s_tail[warp][gi][8 + ci] = __int_as_float(bid);
+    // the stage's batch if all of its cells agree, else -1 (slot 16 of every group of the stage)
+    constexpr int SC = s2::kStageCells;
+    const int first = __shfl_sync(0xffffffffu, bid, lane & ~(SC - 1));
+    const unsigned stage_mask = SC >= 32 ? 0xffffffffu : (((1u << (SC & 31)) - 1u) << (lane & ~(SC - 1)));
+    const unsigned agree = __ballot_sync(0xffffffffu, bid == first);
+    if (ci == 0) {
+      s_tail[warp][gi][16] = __int_as_float((agree & stage_mask) == stage_mask ? first : -1);
+      s_tail[warp][gi][17] = s_tail[warp][gi][18] = s_tail[warp][gi][19] = 0.f;
+    }
+  }
+  __syncwarp();
+  // ---- fragments: lane = (grp, q) of the MMA layouts ----------------------------------------------------------------------
+  const int grp = lane >> 2, q = lane & 3;
+  const int fc = fwd_cell(grp);
+  const int tail = table_tail(H, P.velo != 0);
+  for (int g = 0; g < kTab4Groups; ++g) {
+    const long long group = group0 + g;
+    if (group >= P.n_groups) break;
+    float4* out = reinterpret_cast<float4*>(P.tab + group * P.tabg);
+    const float(*z)[kGroupCells][kTab4Pitch] = sv[warp][g];
+    // forward sections: {TF32 hi of b0 (k = q, n = grp), b1 (k = q + 4); FP16 pairs {y(2q), y(2q+1)} and their lo parts}; column n
+    // is cell fwd_cell(n)
+    auto fwd = [&](int sec_out, int sec) {
+      const float* zc = z[sec][fc];
+      const float x0 = zc[q], x1 = zc[q + 4], y0 = zc[2 * q], y1 = zc[2 * q + 1];
+      out[sec_out * 32 + lane] = make_float4(__uint_as_float(tf32_rna(x0)), __uint_as_float(tf32_rna(x1)),
+                                             __uint_as_float(pack_f16(y0, y1)),
+                                             __uint_as_float(pack_f16(tf32_lo(y0), tf32_lo(y1))));
+    };
+    // backward sections (3xTF32): k runs over cells: b0 (cell q, n = slot grp), b1 (cell q + 4): {hi, hi, lo, lo}
+    auto bwd = [&](int sec_out, int sec, bool clear_spare) {
+      float z0 = z[sec][q][grp], z1 = z[sec][q + 4][grp];
+      if (clear_spare && grp == K) z0 = z1 = 0.f;
+      out[sec_out * 32 + lane] =
+          make_float4(__uint_as_float(tf32_rna(z0)), __uint_as_float(tf32_rna(z1)), tf32_lo(z0), tf32_lo(z1));
+    };
+    fwd(SEC_F0, 0);
+    fwd(SEC_F1, 1);
+    bwd(SEC_B0, 0, true);
+    if (P.velo) {
+      fwd(SEC_F2, 2);
+      bwd(SEC_B1, 3, false);
+    }
+    if (lane < 20) P.tab[group * P.tabg + tail + lane] = s_tail[warp][g][lane];
+  }
+}
+
 // ======================================================================================================
 // Per-cell epilogue: sum the gene-tile partials, add the omega(phi) path to d/dphi, reduce d/dnu_omega.
 // ======================================================================================================
@@ -1076,7 +1211,7 @@ static int run2(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_by
   {
     CellParams cp{p->phi, p->cf, p->Nb > 0 ? p->batch_id : nullptr, p->cond_id, velo ? p->nu_omega : nullptr,
                   tab,    p->Nc, pl.n_groups, p->H, p->Hw, p->Nx, velo ? 1 : 0, pl.tabg, 1};
-    const unsigned n_table_blocks = (unsigned)((pl.n_groups + kTabWarps - 1) / kTabWarps);
+    const unsigned n_table_blocks = (unsigned)((pl.n_groups + kTabWarps * kTab4Groups - 1) / (kTabWarps * kTab4Groups));
     const unsigned n_spec_blocks = (unsigned)((p->Ng + kEpiGenes - 1) / kEpiGenes);
     cp.n_spec_blocks = n_spec_blocks;
     cp.spec_S = p->spec_S;
@@ -1084,7 +1219,7 @@ static int run2(const vcb_problem_t* p, bool velo, void* workspace, size_t ws_by
     cp.shape_inv = p->shape_inv;
     cp.spec_out = spec_pre;
     cp.Ng = p->Ng;
-    vcb_cell_tables_kernel<<<n_table_blocks + n_spec_blocks, kTabWarps * 32, 0, st>>>(cp);
+    vcb_cell_tables4_kernel<<<n_table_blocks + n_spec_blocks, kTabWarps * 32, 0, st>>>(cp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
