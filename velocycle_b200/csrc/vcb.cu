@@ -467,14 +467,19 @@ __device__ void spectrum_block(const CellParams& P, unsigned block) {
 
 __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel(const GeneEpiParams P) {
   __shared__ double s_rows[kEpiMaxRows][kEpiGenes];
-  __shared__ double s_spec[4][kEpiLanes][kEpiGenes];
   const int gx = threadIdx.x % kEpiGenes, ly = threadIdx.x / kEpiGenes;
   const long long g = (long long)blockIdx.x * kEpiGenes + gx;
   const int K = 2 * P.H + 1;
   const int ROWS = ROW_DNU + K;
   const bool valid = g < P.Ng;
 
-  __shared__ double s_part[kEpiLanes][kEpiGenes];
+  // per-split partial rows -> per-gene sums: every thread first sums its share of the splits for ALL rows (independent loads, no
+  // barrier in between: the row-by-row version with two barriers per row was a 14-deep latency chain), then thread (row, gene)
+  // adds the kEpiLanes partials of its row in a fixed order (deterministic)
+  __shared__ double s_rowpart[kEpiMaxRows][kEpiLanes][kEpiGenes];
+  double(*s_part)[kEpiGenes] = s_rowpart[0];               // reused by the batch loop below
+  double(*s_spec)[kEpiLanes][kEpiGenes] = &s_rowpart[1];   // and rows 1..4 by the spectrum sums (after the barrier)
+  static_assert(kEpiMaxRows >= 5, "s_spec aliases rows 1..4");
   for (int row = 0; row < ROWS; ++row) {
     const bool used = (row == ROW_AS || row == ROW_LS) || (P.velo && (row == ROW_AU || row == ROW_LU)) ||
                       (P.velo && P.grad && (row == ROW_GU || row == ROW_W)) || (P.lginline && row == ROW_PSI) ||
@@ -485,15 +490,15 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
       const long long stride = (long long)ROWS * P.ld;
       for (int sidx = ly; sidx < P.n_split; sidx += kEpiLanes) s += (double)src[sidx * stride];
     }
-    s_part[ly][gx] = s;
-    __syncthreads();
-    if (ly == 0) {  // fixed summation order: deterministic
-      double t = 0.0;
-      for (int l = 0; l < kEpiLanes; ++l) t += s_part[l][gx];
-      s_rows[row][gx] = t;
-    }
-    __syncthreads();
+    s_rowpart[row][ly][gx] = s;
   }
+  __syncthreads();
+  for (int row = ly; row < ROWS; row += kEpiLanes) {
+    double t = 0.0;
+    for (int l = 0; l < kEpiLanes; ++l) t += s_rowpart[row][l][gx];
+    s_rows[row][gx] = t;
+  }
+  __syncthreads();
   // vcb_stream2: d/dDelta-nu[b][g] = fixed-order sum of the per-split batch sums; their total is d/dnu_0
   double dnu0_v2 = 0.0;
   if (P.v2 && P.grad && P.Nb > 0 && P.dnu_acc != nullptr) {
