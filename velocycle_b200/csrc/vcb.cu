@@ -480,17 +480,29 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
   double(*s_part)[kEpiGenes] = s_rowpart[0];               // reused by the batch loop below
   double(*s_spec)[kEpiLanes][kEpiGenes] = &s_rowpart[1];   // and rows 1..4 by the spectrum sums (after the barrier)
   static_assert(kEpiMaxRows >= 5, "s_spec aliases rows 1..4");
-  for (int row = 0; row < ROWS; ++row) {
-    const bool used = (row == ROW_AS || row == ROW_LS) || (P.velo && (row == ROW_AU || row == ROW_LU)) ||
-                      (P.velo && P.grad && (row == ROW_GU || row == ROW_W)) || (P.lginline && row == ROW_PSI) ||
-                      (P.grad && row >= ROW_DNU);
-    double s = 0.0;
-    if (valid && used) {
-      const float* src = P.genepart + (long long)row * P.ld + g;
-      const long long stride = (long long)ROWS * P.ld;
-      for (int sidx = ly; sidx < P.n_split; sidx += kEpiLanes) s += (double)src[sidx * stride];
+  {
+    unsigned used = 0;  // bit per row
+    for (int row = 0; row < ROWS; ++row)
+      if ((row == ROW_AS || row == ROW_LS) || (P.velo && (row == ROW_AU || row == ROW_LU)) ||
+          (P.velo && P.grad && (row == ROW_GU || row == ROW_W)) || (P.lginline && row == ROW_PSI) || (P.grad && row >= ROW_DNU))
+        used |= 1u << row;
+    if (!valid) used = 0;
+    double acc[kEpiMaxRows];
+#pragma unroll
+    for (int row = 0; row < kEpiMaxRows; ++row) acc[row] = 0.0;
+    const long long stride = (long long)ROWS * P.ld;
+    // all rows of one split are loaded before any is added: ~14 independent loads in flight per thread instead of one
+    for (int sidx = ly; sidx < P.n_split; sidx += kEpiLanes) {
+      const float* src = P.genepart + sidx * stride + g;
+      float v[kEpiMaxRows];
+#pragma unroll
+      for (int row = 0; row < kEpiMaxRows; ++row) v[row] = (used >> row) & 1u ? __ldg(src + (long long)row * P.ld) : 0.f;
+#pragma unroll
+      for (int row = 0; row < kEpiMaxRows; ++row) acc[row] += (double)v[row];
     }
-    s_rowpart[row][ly][gx] = s;
+#pragma unroll
+    for (int row = 0; row < kEpiMaxRows; ++row)
+      if (row < ROWS) s_rowpart[row][ly][gx] = acc[row];
   }
   __syncthreads();
   for (int row = ly; row < ROWS; row += kEpiLanes) {
@@ -592,17 +604,27 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
   }
   if (blockIdx.x == 0 && P.velo && P.grad && P.d_nu_omega != nullptr) {
     const int n = P.Nx * (2 * P.Hw + 1);
-    // fixed-order sum of the cell epilogue's per-block partials: thread t takes blocks t, t+T, ...; then T partials
-    __shared__ double s_red[kEpiGenes * kEpiLanes];
-    for (int i = 0; i < n; ++i) {
-      double t = 0.0;
-      for (int b = threadIdx.x; b < P.n_cell_blocks; b += blockDim.x) t += P.dnw_part[(size_t)b * n + i];
-      s_red[threadIdx.x] = t;
+    // fixed-order sum of the cell epilogue's per-block partials, four values at a time: thread t takes blocks t, t+T, ... (the
+    // four loads of a block are contiguous), a shuffle tree adds the lanes, then the warps' sums in warp order (deterministic)
+    __shared__ double s_red[kEpiGenes * kEpiLanes / 32][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i0 = 0; i0 < n; i0 += 4) {
+      double t[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int b = threadIdx.x; b < P.n_cell_blocks; b += blockDim.x) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (i0 + j < n) t[j] += P.dnw_part[(size_t)b * n + i0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        for (int o = 16; o > 0; o >>= 1) t[j] += __shfl_xor_sync(0xffffffffu, t[j], o);
+        if (lane == 0) s_red[warp][j] = t[j];
+      }
       __syncthreads();
-      if (threadIdx.x == 0) {
+      if (threadIdx.x < 4 && i0 + threadIdx.x < n) {
         double tot = 0.0;
-        for (int j = 0; j < (int)blockDim.x; ++j) tot += s_red[j];
-        P.d_nu_omega[i] = (float)tot;
+        for (int w = 0; w < nwarps; ++w) tot += s_red[w][threadIdx.x];
+        P.d_nu_omega[i0 + threadIdx.x] = (float)tot;
       }
       __syncthreads();
     }
