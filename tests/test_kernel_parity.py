@@ -99,6 +99,8 @@ SHAPES = [
     (64, 128, 0, 0, 1, 1),      # H = 0: constant-only basis
     (130, 40, 4, 2, 2, 3),
     (97, 33, 5, 5, 1, 2),       # maximum harmonics compiled in
+    (203, 50, 2, 5, 2, 2),      # round-2 path (H <= 3) with more angular-speed harmonics than the table recurrence holds
+    (41, 36, 3, 3, 1, 3),
 ]
 
 
