@@ -578,11 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       set_batch(cur_b);
     }
     if (stage_b >= 0) {
-#ifdef VCB_EXP_NOUNROLL
-#pragma unroll 1
-#else
 #pragma unroll
-#endif
       for (int h = 0; h < kGPS; ++h) do_group(BoolTag<false>{}, h, tb_stage, part_stage);
     } else {
       for (int h = 0; h < kGPS; ++h) do_group(BoolTag<true>{}, h, tb_stage, part_stage);
