@@ -40,7 +40,11 @@ constexpr int kGPS = 2;
 constexpr int kStageCells = kGPS * kGroupCells;  // 16
 constexpr int kD = 4;                            // count groups in flight per warp
 constexpr int kMaxNS = 8;                        // table-ring depth limit (mbarrier slots)
+#ifdef VCB_EXP_THREADS
+constexpr int kThreads = VCB_EXP_THREADS;
+#else
 constexpr int kThreads = 512;  // 16 warps x 128 registers: 20-24 warps at 80-96 registers spill and lose 30 % (tried)
+#endif
 constexpr int kHeader = 256;
 // a stage is serviced (table slot refilled, parked cell partials drained) this many stages later
 constexpr int kSvcDist = kGPS >= 4 ? 1 : 2;
