@@ -193,6 +193,26 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
     }
   }
   __syncwarp();
+#ifdef VCB_EXP_REGA
+  // forward A operands and per-gene parameters held in registers (needs the 255-register configuration)
+  uint4 rA0[NT][KS], rA1[NT][KS];
+  float4 rGa[NT], rGb[NT];
+  auto reload_gene_regs = [&]() {
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+      rGa[mt] = s_gene[(mt * 2 + 0) * 8];
+      rGb[mt] = s_gene[(mt * 2 + 1) * 8];
+    }
+  };
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      rA0[mt][ks] = s_aop[((mt * KS + ks) * 2 + 0) * 32];
+      rA1[mt][ks] = s_aop[((mt * KS + ks) * 2 + 1) * 32];
+    }
+  reload_gene_regs();
+#endif
   auto set_batch = [&](int b) {
     __syncwarp();
     if (q == 0) {
@@ -205,6 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       }
     }
     __syncwarp();
+#ifdef VCB_EXP_REGA
+    reload_gene_regs();
+#endif
   };
   // -2 = no batch selected yet (a mixed stage is stamped -1 and must never compare equal); without batches the table kernel
   // stamps every stage with 0
@@ -362,7 +385,11 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
       float Ce[4] = {0.f, 0.f, 0.f, 0.f}, Cd[4] = {0.f, 0.f, 0.f, 0.f}, Cw[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
+#ifdef VCB_EXP_REGA
+        const uint4 a0 = rA0[mt][ks], a1 = rA1[mt][ks];
+#else
         const uint4 a0 = s_aop[((mt * KS + ks) * 2 + 0) * 32], a1 = s_aop[((mt * KS + ks) * 2 + 1) * 32];
+#endif
         const uint32_t am[4] = {a0.x, a0.y, a0.z, a0.w}, ax[4] = {a1.x, a1.y, a1.z, a1.w};
 #ifdef VCB_EXP_NOFWD
         Ce[0] = __uint_as_float(am[0]) * tb[q]; Ce[1] = __uint_as_float(am[1]) * tb[q]; Ce[2] = __uint_as_float(am[2]) * tb[q]; Ce[3] = __uint_as_float(am[3]) * tb[q];
@@ -374,11 +401,19 @@ __global__ void __launch_bounds__(kThreads, 1) vcb_stream2_kernel(const Params P
         if (NEED_E) mma_split_fwd(Cw, am, ax, tb4[(SEC_F2 * KS + ks) * 32 + lane]);
 #endif
       }
+#ifdef VCB_EXP_REGA
+      const float4 ga = rGa[mt];
+#else
       const float4 ga = s_gene[(mt * 2 + 0) * 8];
+#endif
       const float2 nr_mt = f2(ga.x, ga.y);
       float2 gam_mt = one2, invb_mt = one2;
       if (VELO) {
+#ifdef VCB_EXP_REGA
+        const float4 gb = rGb[mt];
+#else
         const float4 gb = s_gene[(mt * 2 + 1) * 8];
+#endif
         gam_mt = f2(gb.x, gb.y);
         invb_mt = f2(gb.z, gb.w);
       }
