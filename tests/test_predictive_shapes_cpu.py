@@ -75,6 +75,19 @@ def test_without_a_guide_the_default_is_the_sites_outside_the_posterior_samples(
     assert shapes(Predictive(model, posterior_samples=post, return_sites=None)()) == ALL
 
 
+def test_padding_helper_matches_and_leaves_the_rng_alone():
+    """``predictive_padding`` (what the batched posterior draws use to pad their outputs) = the singleton dims of the shapes
+    above, computed without consuming random numbers."""
+    from velocycle_b200.ppl.infer import predictive_padding
+
+    model, guide = make(shim, sdist)
+    torch.manual_seed(5)
+    before = torch.random.get_rng_state()
+    pad = predictive_padding(model, guide)
+    assert torch.equal(torch.random.get_rng_state(), before)
+    assert pad == {"nu": 1, "g": 1, "d": 0, "xy": 2, "phi": 3, "S": 1}
+
+
 def _pyro():
     try:
         import pyro  # noqa: F401
