@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kEpiGenes* kEpiLanes) vcb_gene_epilogue_kernel
   {
     unsigned used = 0;  // bit per row
     for (int row = 0; row < ROWS; ++row)
-      if ((row == ROW_AS || row == ROW_LS) || (P.velo && (row == ROW_AU || row == ROW_LU)) ||
+      if ((row == ROW_AS || row == ROW_LS) || (P.velo && (row == ROW_AU || (row == ROW_LU && !P.v2))) ||  // (v2 folds LU into ROW_LS)
           (P.velo && P.grad && (row == ROW_GU || row == ROW_W)) || (P.lginline && row == ROW_PSI) || (P.grad && row >= ROW_DNU))
         used |= 1u << row;
     if (!valid) used = 0;
